@@ -1,0 +1,166 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (prysm @ /root/reference).
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+The reference is Python and cannot travel to the GPU box, so its outputs on seeded inputs
+are committed as small fixtures.  `small.npz` holds complete input/output pairs for every
+hot-path function at test sizes; `full_*.npz` hold windows / strided samples / checksums of
+the reference's fp64 outputs at the BASELINE.json sizes (C1, C2, C3) so that the CUDA path
+can be compared with the real reference at full size without shipping 256 MB arrays.
+"""
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get('PRYSM_REFERENCE', '/root/reference')
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+from prysm.conf import config  # noqa: E402
+from prysm import fttools, propagation, otf, psf  # noqa: E402
+from prysm.propagation import Wavefront  # noqa: E402
+from prysm.coordinates import make_xy_grid, cart_to_polar  # noqa: E402
+from prysm.geometry import circle  # noqa: E402
+from prysm.polynomials import zernike_nm_seq, noll_to_nm, sum_of_2d_modes  # noqa: E402
+from prysm.wavelengths import HeNe  # noqa: E402
+
+config.precision = 64
+
+
+def crand(rng, shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def ref_pupil(N):
+    """SURVEY.md 8(d) builder, executed by the reference's own code in fp64."""
+    x, y = make_xy_grid(N, diameter=10.0)
+    r, t = cart_to_polar(x, y)
+    amp = circle(5.0, r)
+    nms = [noll_to_nm(j) for j in range(2, 38)]
+    coefs = np.random.default_rng(20260923).normal(0, 30.0, 36)
+    opd = sum_of_2d_modes(zernike_nm_seq(nms, r / 5.0, t), coefs)
+    return amp, opd, 10.0 / N
+
+
+def small():
+    rng = np.random.default_rng(20260923)
+    g = {}
+    # --- fft focus family (reference tests/test_propagation.py:24-55 shapes and Qs)
+    for i, (shp, Q) in enumerate((((8, 8), 1), ((8, 8), 2), ((9, 12), 1.5), ((7, 9), 2), ((16, 16), 2),
+                                  ((64, 64), 2), ((12, 5), 3), ((32, 64), 1), ((9, 9), 1))):
+        a = crand(rng, shp)
+        g[f'focus{i}_in'] = a
+        g[f'focus{i}_Q'] = np.float64(Q)
+        g[f'focus{i}_focus'] = propagation.focus(a, Q)
+        g[f'focus{i}_unfocus'] = propagation.unfocus(a, Q)
+        b = crand(rng, g[f'focus{i}_focus'].shape)
+        g[f'focus{i}_gin'] = b
+        g[f'focus{i}_focus_adjoint'] = propagation.focus_adjoint(b, Q)
+        g[f'focus{i}_unfocus_adjoint'] = propagation.unfocus_adjoint(b, Q)
+    # --- Wavefront object path on the seeded pupil at N=64
+    amp, opd, dx = ref_pupil(64)
+    wf = Wavefront.from_amp_and_phase(amp, opd, HeNe, dx)
+    psfwf = wf.focus(100.0, Q=2)
+    g['wf_amp'], g['wf_opd'], g['wf_dx'] = amp, opd, np.float64(dx)
+    g['wf_field'] = wf.data
+    g['wf_psf_field'] = psfwf.data
+    g['wf_psf_dx'] = np.float64(psfwf.dx)
+    g['wf_psf_intensity'] = psfwf.intensity.data
+    back = psfwf.unfocus(100.0, Q=1)
+    g['wf_back_field'], g['wf_back_dx'] = back.data, np.float64(back.dx)
+    mt = otf.mtf_from_psf(psfwf.intensity)
+    g['wf_mtf'], g['wf_mtf_df'] = mt.data, np.float64(mt.dx)
+    g['wf_ptf'] = otf.ptf_from_psf(psfwf.intensity).data
+    g['wf_otf'] = otf.otf_from_psf(psfwf.intensity).data
+    g['wf_centroid'] = np.asarray(psf.centroid(psfwf.intensity.data, psfwf.dx))
+    g['wf_centroid_px'] = np.asarray(psf.centroid(psfwf.intensity.data, unit='pixels'))
+    x, y = make_xy_grid(64, diameter=10.0)
+    g['lens'] = Wavefront.thin_lens(250.0, HeNe, x, y).data
+    # --- angular spectrum (reference tests/test_propagation.py:178-243)
+    f = crand(rng, (24, 32))
+    g['as_in'] = f
+    for Q in (1, 2):
+        g[f'as_Q{Q}'] = propagation.angular_spectrum(f, HeNe, 0.05, 12.5, Q)
+    tf = propagation.angular_spectrum_transfer_function((24, 32), HeNe, 0.05, 12.5)
+    g['as_tf'] = tf
+    g['as_with_tf'] = propagation.angular_spectrum(f, HeNe, 0.05, 12.5, tf=tf)
+    gq = crand(rng, (48, 64))
+    g['as_gin'] = gq
+    g['as_adjoint_Q2'] = propagation.angular_spectrum_adjoint(gq, HeNe, 0.05, 12.5, 2)
+    f9 = crand(rng, (9, 12))
+    g['as9_in'] = f9
+    g['as9_Q1'] = propagation.angular_spectrum(f9, HeNe, 0.05, 3.0, 1)
+    g['as9_Q15'] = propagation.angular_spectrum(f9, HeNe, 0.05, 3.0, 1.5)
+    # --- executors
+    cases = (((16, 16), (8, 8), 2.0, (0.0, 0.0)), ((9, 12), (8, 11), 1.7, (3.0, -2.0)),
+             ((32, 24), (40, 12), 0.9, (0.5, 0.25)), ((64, 64), (32, 32), 3.164, (0.0, 0.0)))
+    for i, (pn, fn, fdx, shift) in enumerate(cases):
+        a = crand(rng, pn)
+        gg = crand(rng, fn)
+        g[f'ex{i}_in'], g[f'ex{i}_gin'] = a, gg
+        g[f'ex{i}_params'] = np.array([0.1, fdx, HeNe, 100.0, shift[0], shift[1]])
+        for kind in ('mdft', 'czt'):
+            ex = propagation.prepare_executor(0.1, pn, fdx, fn, HeNe, 100.0, shift, kind)
+            g[f'ex{i}_{kind}_fwd'] = ex(a)
+            g[f'ex{i}_{kind}_adj'] = ex.adjoint(gg)
+    K = 32
+    pdx = 0.1
+    fdx = HeNe * 100.0 / (pdx * K)
+    for i, (pn, fn) in enumerate((((16, 16), (32, 32)), ((20, 16), (12, 32)))):
+        a = crand(rng, pn)
+        gg = crand(rng, fn)
+        ex = propagation.prepare_executor(pdx, pn, fdx, fn, HeNe, 100.0, (0, 0), 'fftdft')
+        g[f'fd{i}_in'], g[f'fd{i}_gin'] = a, gg
+        g[f'fd{i}_params'] = np.array([pdx, fdx, HeNe, 100.0, 0.0, 0.0])
+        g[f'fd{i}_fwd'], g[f'fd{i}_adj'] = ex(a), ex.adjoint(gg)
+    # --- incoherent sum
+    modes = rng.random((6, 12, 10))
+    wts = rng.random(6)
+    g['modes'], g['weights'], g['modes_sum'] = modes, wts, sum_of_2d_modes(modes, wts)
+    np.savez_compressed(os.path.join(OUT, 'small.npz'), **g)
+    print('small.npz', len(g), 'arrays')
+
+
+def window(a, w):
+    cy, cx = a.shape[0] // 2, a.shape[1] // 2
+    return a[cy - w // 2:cy + w // 2, cx - w // 2:cx + w // 2]
+
+
+def full():
+    # C1: 256^2 -> 512^2 fp64 FFT focus;  C2: 2048^2 -> 4096^2 (fp64 arbiter for the fp32 GPU path)
+    for name, N in (('c1', 256), ('c2', 2048)):
+        amp, opd, dx = ref_pupil(N)
+        wf = Wavefront.from_amp_and_phase(amp, opd, HeNe, dx)
+        ps = wf.focus(100.0, Q=2)
+        I = ps.intensity.data
+        mt = otf.mtf_from_psf(I, ps.dx).data
+        g = dict(N=np.int64(N), psf_dx=np.float64(ps.dx),
+                 field_win=window(ps.data, 64), field_stride=ps.data[::N // 16, ::N // 16],
+                 field_absmax=np.float64(np.abs(ps.data).max()),
+                 I_win=window(I, 64), I_max=np.float64(I.max()), I_sum=np.float64(I.sum()),
+                 I_rowsum=I.sum(axis=1)[::8], I_colsum=I.sum(axis=0)[::8],
+                 E_in=np.float64((np.abs(wf.data) ** 2).sum()),
+                 mtf_win=window(mt, 64), mtf_row=mt[mt.shape[0] // 2, ::8])
+        np.savez_compressed(os.path.join(OUT, f'full_{name}.npz'), **g)
+        print(f'full_{name}.npz written; I_max={I.max():.6e}')
+    # C3: 4096^2 -> 512^2 MDFT (focal_dx = wvl*F#/4)
+    N = 4096
+    amp, opd, dx = ref_pupil(N)
+    wf = Wavefront.from_amp_and_phase(amp, opd, HeNe, dx)
+    fdx = HeNe * (100.0 / 10.0) / 4
+    ex = wf.prepare_executor(100.0, fdx, 512, kind='mdft')
+    out = wf.focus_dft(ex).data
+    g = dict(N=np.int64(N), M=np.int64(512), focal_dx=np.float64(fdx), norm=np.float64(ex.norm),
+             field_win=window(out, 64), field_stride=out[::16, ::16],
+             field_absmax=np.float64(np.abs(out).max()),
+             I_sum=np.float64((np.abs(out) ** 2).sum()))
+    np.savez_compressed(os.path.join(OUT, 'full_c3.npz'), **g)
+    print('full_c3.npz written')
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    small()
+    full()

@@ -1,0 +1,574 @@
+"""CPU oracle for the prysm propagation hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy / scipy.fft restatement of the algorithms on the path named by
+BASELINE.json (prysm.propagation + prysm.fttools + the psf/otf reductions, reference
+v0.22 @ 5008f47).  It is the *checker* for the CUDA product in ``prysm_b200``: only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu-baseline / reference arm
+may import it.  Nothing in ``prysm_b200`` imports this module, and the product has no
+CPU fallback.
+
+Third-party arithmetic: like the reference, the FFT is ``scipy.fft`` (pocketfft) and
+the dense contractions are numpy ``matmul`` (OpenBLAS); prysm pins no versions
+(reference ``pyproject.toml:39-42``); this image has scipy 1.18.1 / numpy 2.3.5.
+
+Parity pin: ``oracle/check_against_reference.py`` runs every function below against
+the unmodified reference imported from /root/reference on seeded inputs (bit-for-bit or
+<= 4 ulp fp64), and ``oracle/make_golden.py`` writes reference outputs to
+``tests/golden/*.npz`` which ``tests/test_oracle_golden.py`` replays on any box.
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+Units follow the reference: wavelength um, pupil dx mm, focal dx um, OPD nm, efl / z mm.
+Arrays are indexed [y, x].
+"""
+import math
+
+import numpy as np
+from scipy import fft as sfft
+
+# --------------------------------------------------------------------------------------
+# grids, pad, crop  (prysm/fttools.py:13-125)
+# --------------------------------------------------------------------------------------
+
+
+def fftrange(n, dtype=np.float64):
+    """Integer grid whose zero sits at index n//2.  prysm/fttools.py:13-15."""
+    lo = -(n // 2)
+    return np.arange(lo, lo + n, dtype=dtype)
+
+
+def next_fast_len(n):
+    """5-smooth length used by CZT.  prysm/fttools.py:23-31 (-> scipy.fft.next_fast_len)."""
+    return sfft.next_fast_len(n)
+
+
+def fftfreq(n, d=1.0, dtype=np.float64):
+    """Unshifted DFT sample frequencies cast to the working precision.  prysm/fttools.py:34-40."""
+    return sfft.fftfreq(n, d).astype(dtype)
+
+
+def padded_shape(shape, Q):
+    """ceil(s*Q) per axis.  prysm/fttools.py:75."""
+    return tuple(math.ceil(s * Q) for s in shape)
+
+
+def pad_offsets(in_shape, out_shape):
+    """Insertion offset ceil((out-in)/2) per axis.  prysm/fttools.py:87-88."""
+    return tuple(math.ceil((o - i) / 2) for o, i in zip(out_shape, in_shape))
+
+
+def pad2d(a, Q=2, value=0, out_shape=None):
+    """Centred constant pad.  prysm/fttools.py:43-100 (mode='constant' branch)."""
+    if Q == 1 and out_shape is None:
+        return a
+    if out_shape is None:
+        out_shape = padded_shape(a.shape, Q)
+    elif isinstance(out_shape, int):
+        out_shape = (out_shape,) * a.ndim
+    off = pad_offsets(a.shape, out_shape)
+    out = np.full(out_shape, value, dtype=a.dtype) if value != 0 else np.zeros(out_shape, dtype=a.dtype)
+    out[tuple(slice(o, o + s) for o, s in zip(off, a.shape))] = a
+    return out
+
+
+def crop_center(a, out_shape):
+    """Inverse of pad2d: window starting at ceil((in-out)/2).  prysm/fttools.py:103-125."""
+    if isinstance(out_shape, int):
+        out_shape = (out_shape, out_shape)
+    off = pad_offsets(out_shape, a.shape)
+    return a[tuple(slice(o, o + s) for o, s in zip(off, out_shape))]
+
+
+def shape_before_pad(shape, Q):
+    """int(s // Q) per axis.  prysm/propagation/_kernels.py:14-18."""
+    if Q == 1:
+        return tuple(shape)
+    return tuple(int(s // Q) for s in shape)
+
+
+def adjoint_pad2d(a, Q):
+    """prysm/propagation/_kernels.py:21-26."""
+    tgt = shape_before_pad(a.shape, Q)
+    return a if tgt == tuple(a.shape) else crop_center(a, tgt)
+
+
+# --------------------------------------------------------------------------------------
+# FFT focus / unfocus  (prysm/propagation/fft.py:7-85, 112-155)
+# --------------------------------------------------------------------------------------
+
+
+def _centered_ft2(a, inverse):
+    f = sfft.ifft2 if inverse else sfft.fft2
+    return sfft.fftshift(f(sfft.ifftshift(a), norm='ortho'))
+
+
+def focus(w, Q):
+    """pupil -> psf: fftshift(fft2(ifftshift(pad(w,Q)), ortho)).  prysm/propagation/fft.py:7-25."""
+    return _centered_ft2(pad2d(w, Q) if Q != 1 else w, inverse=False)
+
+
+def unfocus(w, Q):
+    """psf -> pupil, same with ifft2.  prysm/propagation/fft.py:48-65."""
+    return _centered_ft2(pad2d(w, Q) if Q != 1 else w, inverse=True)
+
+
+def focus_adjoint(g, Q):
+    """prysm/propagation/fft.py:28-45."""
+    return adjoint_pad2d(_centered_ft2(g, inverse=True), Q)
+
+
+def unfocus_adjoint(g, Q):
+    """prysm/propagation/fft.py:68-85."""
+    return adjoint_pad2d(_centered_ft2(g, inverse=False), Q)
+
+
+def pupil_sample_to_psf_sample(pupil_dx, samples, wavelength, efl):
+    """efl*wvl/(dx*K).  prysm/propagation/fft.py:112-132."""
+    return (efl * wavelength) / (pupil_dx * samples)
+
+
+def psf_sample_to_pupil_sample(psf_dx, samples, wavelength, efl):
+    """prysm/propagation/fft.py:135-155."""
+    return (efl * wavelength) / (psf_dx * samples)
+
+
+# --------------------------------------------------------------------------------------
+# wavefront synthesis and intensity  (prysm/propagation/wavefront.py:59-151, _kernels.py:40-43)
+# --------------------------------------------------------------------------------------
+
+
+def phase_prefix(wavelength):
+    """i*2pi/wvl[um]/1e3: OPD[nm] -> radians.  prysm/propagation/_kernels.py:40-43."""
+    return 1j * 2 * np.pi / wavelength / 1e3
+
+
+def from_amp_and_phase(amp, opd_nm, wavelength):
+    """A*exp(prefix*OPD).  prysm/propagation/wavefront.py:59-79."""
+    if opd_nm is None:
+        return amp
+    return amp * np.exp(phase_prefix(wavelength) * opd_nm)
+
+
+def phase_screen(opd_nm, wavelength):
+    """prysm/propagation/wavefront.py:82-96."""
+    return np.exp(phase_prefix(wavelength) * opd_nm)
+
+
+def thin_lens(f, wavelength, x, y):
+    """exp(-i*2pi/wvl_mm * r^2/(2f)).  prysm/propagation/wavefront.py:99-144."""
+    w = wavelength / 1e3
+    return np.exp((-1j * 2 * np.pi / w) * ((x * x + y * y) / (2 * f)))
+
+
+def intensity(field):
+    """re^2+im^2.  prysm/propagation/wavefront.py:147-151."""
+    return field.real * field.real + field.imag * field.imag
+
+
+# --------------------------------------------------------------------------------------
+# angular spectrum  (prysm/propagation/angular_spectrum.py:9-114)
+# --------------------------------------------------------------------------------------
+
+
+def angular_spectrum_vectors(shape, wvl, dx, z, dtype=np.float64):
+    """The two 1-D factors (tfy, tfx) of the separable Fresnel transfer function.
+
+    prysm/propagation/angular_spectrum.py:102-113: wvl -> mm, k = fftfreq(s, dx).astype(P),
+    exp(-i*pi*wvl*z*k^2) per axis.
+    """
+    if isinstance(shape, int):
+        shape = (shape, shape)
+    wmm = wvl / 1e3
+    ky, kx = (sfft.fftfreq(s, dx).astype(dtype) for s in shape)
+    pre = -1j * np.pi * wmm * z
+    return np.exp(pre * (ky * ky)), np.exp(pre * (kx * kx))
+
+
+def angular_spectrum_transfer_function(shape, wvl, dx, z, dtype=np.float64):
+    """outer(tfy, tfx).  prysm/propagation/angular_spectrum.py:82-114."""
+    ty, tx = angular_spectrum_vectors(shape, wvl, dx, z, dtype)
+    return np.outer(ty, tx)
+
+
+def angular_spectrum(field, wvl, dx, z, Q=2, tf=None, dtype=np.float64):
+    """ifft2(fft2(pad(field)) * tf); result stays padded.  prysm/propagation/angular_spectrum.py:9-42."""
+    if tf is not None:
+        return sfft.ifft2(sfft.fft2(field) * tf)
+    if Q != 1:
+        field = pad2d(field, Q)
+    tf = angular_spectrum_transfer_function(field.shape, wvl, dx, z, dtype)
+    return sfft.ifft2(sfft.fft2(field) * tf)
+
+
+def angular_spectrum_adjoint(g, wvl, dx, z, Q=2, tf=None, dtype=np.float64):
+    """prysm/propagation/angular_spectrum.py:45-79."""
+    if tf is None:
+        tf = angular_spectrum_transfer_function(g.shape, wvl, dx, z, dtype)
+        tgt = shape_before_pad(g.shape, Q)
+    else:
+        tgt = tuple(g.shape)
+    out = sfft.ifft2(sfft.fft2(g) * np.conj(tf))
+    return out if tgt == tuple(g.shape) else crop_center(out, tgt)
+
+
+# --------------------------------------------------------------------------------------
+# fixed-sampling executors  (prysm/fttools.py:155-535, prysm/propagation/dft.py:12-117)
+# --------------------------------------------------------------------------------------
+
+
+def coordinates_for_focus(pupil_dx, pupil_samples, focal_dx, focal_samples, wavelength, efl,
+                          focal_shift=(0, 0), dtype=np.float64):
+    """x, y [mm] and fx, fy [1/mm].  prysm/propagation/dft.py:12-66."""
+    if isinstance(pupil_samples, int):
+        pupil_samples = (pupil_samples, pupil_samples)
+    if isinstance(focal_samples, int):
+        focal_samples = (focal_samples, focal_samples)
+    pny, pnx = pupil_samples
+    fny, fnx = focal_samples
+    sx, sy = focal_shift
+    x = fftrange(pnx, dtype) * pupil_dx
+    y = fftrange(pny, dtype) * pupil_dx
+    inv = 1.0 / (wavelength * efl)
+    fx = (fftrange(fnx, dtype) * focal_dx + sx) * inv
+    fy = (fftrange(fny, dtype) * focal_dx + sy) * inv
+    return x, y, fx, fy
+
+
+class MDFT:
+    """Dense two-sided matrix DFT.  prysm/fttools.py:155-232."""
+
+    def __init__(self, x, y, fx, fy, sign=-1, norm=1.0):
+        c = sign * 2j * np.pi
+        self.Ex = np.exp(c * np.outer(fx, x))
+        self.Ey = np.exp(c * np.outer(fy, y))
+        self.norm = norm
+        Nx, Ny, Mx, My = len(x), len(y), len(fx), len(fy)
+        # cheaper association first, prysm/fttools.py:198-199
+        self._forward_left_first = My * Nx * (Ny + Mx) <= Ny * Mx * (Nx + My)
+        self._adjoint_left_first = Ny * Mx * (My + Nx) <= My * Nx * (Mx + Ny)
+
+    def __call__(self, a):
+        if self._forward_left_first:
+            return ((self.Ey @ a) @ self.Ex.T) * self.norm
+        return (self.Ey @ (a @ self.Ex.T)) * self.norm
+
+    def adjoint(self, g):
+        EyH = self.Ey.conj().T
+        ExC = self.Ex.conj()
+        if self._adjoint_left_first:
+            return ((EyH @ g) @ ExC) * self.norm
+        return (EyH @ (g @ ExC)) * self.norm
+
+    def nbytes(self):
+        return self.Ex.nbytes + self.Ey.nbytes
+
+
+def _czt_axis_basis(N, M, K, shift, alpha, rdtype, cdtype, sign):
+    """Chirps a(m), b(n) and the kernel spectrum H.  prysm/fttools.py:372-389."""
+    n = fftrange(N, rdtype)
+    m = fftrange(M, rdtype)
+    q = m + shift
+    c = sign * 1j * np.pi * alpha
+    a = np.exp(c * q * q)
+    b = np.exp(c * n * n)
+    d = np.arange(m[0] - n[-1], m[-1] - n[0] + 1, dtype=rdtype)
+    h = np.zeros(K, dtype=cdtype)
+    h[:len(d)] = np.exp(-c * (d + shift) * (d + shift))
+    return sfft.fft(h), b, a
+
+
+class CZT:
+    """Bluestein chirp-z with the MDFT interface.  prysm/fttools.py:235-369."""
+
+    def __init__(self, x, y, fx, fy, sign=-1, norm=1.0, rdtype=np.float64):
+        if sign not in (-1, 1):
+            raise ValueError(f'sign must be -1 or +1, got {sign}')
+        cdtype = np.result_type(rdtype, 1j)
+        self.sign, self.norm = sign, norm
+        Nx, Mx, Ny, My = len(x), len(fx), len(y), len(fy)
+        dx, dfx = float(x[1] - x[0]), float(fx[1] - fx[0])
+        dy, dfy = float(y[1] - y[0]), float(fy[1] - fy[0])
+        sh_x = float(fx[Mx // 2]) / dfx
+        sh_y = float(fy[My // 2]) / dfy
+        Kx, Ky = next_fast_len(Nx + Mx - 1), next_fast_len(Ny + My - 1)
+        Hx, bx, ax = _czt_axis_basis(Nx, Mx, Kx, sh_x, dx * dfx, rdtype, cdtype, sign)
+        Hy, by, ay = _czt_axis_basis(Ny, My, Ky, sh_y, dy * dfy, rdtype, cdtype, sign)
+        c = sign * 2j * np.pi
+        self.bx, self.Hx, self.ax = bx, Hx, ax
+        self.by, self.Hy, self.ay = by[:, None], Hy[:, None], ay[:, None]
+        self.px = np.exp(c * float(x[Nx // 2]) * fx)
+        self.py = np.exp(c * float(y[Ny // 2]) * fy)[:, None]
+        self.N, self.M, self.K = (Ny, Nx), (My, Mx), (Ky, Kx)
+        cost_x_first = Ny * Kx * math.log2(Kx) + Mx * Ky * math.log2(Ky)
+        cost_y_first = Nx * Ky * math.log2(Ky) + My * Kx * math.log2(Kx)
+        self._x_first = cost_x_first <= cost_y_first
+
+    def _along_x(self, o):
+        (Ny, Nx), (My, Mx), (Ky, Kx) = self.N, self.M, self.K
+        o = sfft.ifft(sfft.fft(o, Kx, axis=1) * self.Hx, axis=1)
+        return o[:, Nx - 1:Nx - 1 + Mx] * self.ax * self.px
+
+    def _along_y(self, o):
+        (Ny, Nx), (My, Mx), (Ky, Kx) = self.N, self.M, self.K
+        o = sfft.ifft(sfft.fft(o, Ky, axis=0) * self.Hy, axis=0)
+        return o[Ny - 1:Ny - 1 + My] * self.ay * self.py
+
+    def __call__(self, a):
+        o = a * self.bx * self.by
+        o = self._along_y(self._along_x(o)) if self._x_first else self._along_x(self._along_y(o))
+        return o * self.norm
+
+    def adjoint(self, g):
+        (Ny, Nx), (My, Mx), (Ky, Kx) = self.N, self.M, self.K
+        o = g * self.px.conj() * self.py.conj() * self.ax.conj() * self.ay.conj()
+
+        def back_y(o):
+            t = np.zeros((Ky, o.shape[1]), dtype=o.dtype)
+            t[Ny - 1:Ny - 1 + My] = o
+            return sfft.ifft(sfft.fft(t, axis=0) * self.Hy.conj(), axis=0)[:Ny]
+
+        def back_x(o):
+            t = np.zeros((o.shape[0], Kx), dtype=o.dtype)
+            t[:, Nx - 1:Nx - 1 + Mx] = o
+            return sfft.ifft(sfft.fft(t, axis=1) * self.Hx.conj(), axis=1)[:, :Nx]
+
+        o = back_x(back_y(o)) if self._x_first else back_y(back_x(o))
+        return o * self.bx.conj() * self.by.conj() * self.norm
+
+    def nbytes(self):
+        return sum(v.nbytes for v in (self.by, self.bx, self.Hy, self.Hx, self.ay, self.ax, self.px, self.py))
+
+
+def _uniform_spacing(v, name, rdtype):
+    """prysm/fttools.py:484-497."""
+    if len(v) < 2:
+        raise ValueError(f'{name} must contain at least two samples')
+    sp = float(v[1] - v[0])
+    if sp == 0:
+        raise ValueError(f'{name} must have nonzero spacing')
+    tol = 32 * np.finfo(rdtype).eps
+    scale = max(1.0, abs(float(v[0])), abs(float(v[-1])), abs(sp))
+    if not bool(np.allclose(np.diff(v), sp, rtol=tol, atol=tol * scale)):
+        raise ValueError(f'{name} must be uniformly spaced')
+    return sp
+
+
+def _fft_compatible_length(alpha, N, M, name, rdtype):
+    """prysm/fttools.py:500-514."""
+    inv = 1 / abs(alpha)
+    K = round(inv)
+    tol = 32 * np.finfo(rdtype).eps
+    if not math.isclose(inv, K, rel_tol=tol, abs_tol=tol):
+        raise ValueError(f'{name} spacings are not FFT-compatible: '
+                         'abs(input spacing * output spacing) must be 1/integer')
+    if K < max(N, M):
+        raise ValueError(f'{name} requires FFT length {K}, smaller than input/output length {max(N, M)}')
+    return K
+
+
+class FFTDFT:
+    """One FFT per axis when dx*dfx = +-1/K.  prysm/fttools.py:392-481, 517-535."""
+
+    def __init__(self, x, y, fx, fy, sign=-1, norm=1.0, rdtype=np.float64):
+        if sign not in (-1, 1):
+            raise ValueError(f'sign must be -1 or +1, got {sign}')
+        Nx, Ny, Mx, My = len(x), len(y), len(fx), len(fy)
+        dx, dy = _uniform_spacing(x, 'x', rdtype), _uniform_spacing(y, 'y', rdtype)
+        dfx, dfy = _uniform_spacing(fx, 'fx', rdtype), _uniform_spacing(fy, 'fy', rdtype)
+        Kx = _fft_compatible_length(dx * dfx, Nx, Mx, 'x/fx', rdtype)
+        Ky = _fft_compatible_length(dy * dfy, Ny, My, 'y/fy', rdtype)
+        c = sign * 2j * np.pi
+        self.pre_x = np.exp(c * np.arange(Nx, dtype=rdtype) * dx * float(fx[0]))
+        self.pre_y = np.exp(c * np.arange(Ny, dtype=rdtype) * dy * float(fy[0]))[:, None]
+        self.post_x = np.exp(c * float(x[0]) * fx)
+        self.post_y = np.exp(c * float(y[0]) * fy)[:, None]
+        self.N, self.M, self.K = (Ny, Nx), (My, Mx), (Ky, Kx)
+        self.dir_x = sign if dx * dfx > 0 else -sign
+        self.dir_y = sign if dy * dfy > 0 else -sign
+        self.norm = norm
+        cost_x_first = Ny * Kx * math.log2(Kx) + Mx * Ky * math.log2(Ky)
+        cost_y_first = Nx * Ky * math.log2(Ky) + My * Kx * math.log2(Kx)
+        self._x_first = cost_x_first <= cost_y_first
+
+    @staticmethod
+    def _fwd(a, K, axis, d):
+        return sfft.fft(a, K, axis=axis) if d == -1 else sfft.ifft(a, K, axis=axis) * K
+
+    @staticmethod
+    def _bwd(a, K, N, axis, d):
+        shp = list(a.shape)
+        shp[axis] = K
+        t = np.zeros(shp, dtype=a.dtype)
+        sl = [slice(None)] * a.ndim
+        sl[axis] = slice(0, a.shape[axis])
+        t[tuple(sl)] = a
+        o = sfft.ifft(t, axis=axis) * K if d == -1 else sfft.fft(t, axis=axis)
+        sl[axis] = slice(0, N)
+        return o[tuple(sl)]
+
+    def __call__(self, a):
+        (Ny, Nx), (My, Mx), (Ky, Kx) = self.N, self.M, self.K
+        o = a * self.pre_x * self.pre_y
+        if self._x_first:
+            o = self._fwd(o, Kx, 1, self.dir_x)[:, :Mx]
+            o = self._fwd(o, Ky, 0, self.dir_y)[:My]
+        else:
+            o = self._fwd(o, Ky, 0, self.dir_y)[:My]
+            o = self._fwd(o, Kx, 1, self.dir_x)[:, :Mx]
+        return o * self.post_x * self.post_y * self.norm
+
+    def adjoint(self, g):
+        (Ny, Nx), (My, Mx), (Ky, Kx) = self.N, self.M, self.K
+        o = g * self.post_x.conj() * self.post_y.conj()
+        if self._x_first:
+            o = self._bwd(o, Ky, Ny, 0, self.dir_y)
+            o = self._bwd(o, Kx, Nx, 1, self.dir_x)
+        else:
+            o = self._bwd(o, Kx, Nx, 1, self.dir_x)
+            o = self._bwd(o, Ky, Ny, 0, self.dir_y)
+        return o * self.pre_x.conj() * self.pre_y.conj() * self.norm
+
+    def nbytes(self):
+        return sum(v.nbytes for v in (self.pre_x, self.pre_y, self.post_x, self.post_y))
+
+
+def prepare_executor(pupil_dx, pupil_samples, focal_dx, focal_samples, wavelength, efl,
+                     focal_shift=(0, 0), kind='mdft', rdtype=np.float64):
+    """prysm/propagation/dft.py:69-117: norm = pupil_dx*focal_dx/(wvl*efl) baked in."""
+    x, y, fx, fy = coordinates_for_focus(pupil_dx, pupil_samples, focal_dx, focal_samples,
+                                         wavelength, efl, focal_shift, rdtype)
+    norm = (pupil_dx * focal_dx) / (wavelength * efl)
+    if kind == 'mdft':
+        op = MDFT(x, y, fx, fy, -1, norm)
+    elif kind == 'czt':
+        op = CZT(x, y, fx, fy, -1, norm, rdtype)
+    elif kind == 'fftdft':
+        op = FFTDFT(x, y, fx, fy, -1, norm, rdtype)
+    else:
+        raise ValueError(f"kind must be 'mdft', 'czt', or 'fftdft', got {kind!r}")
+    op.pupil_dx, op.focal_dx = pupil_dx, focal_dx
+    return op
+
+
+def unit_cell_focal_grid(pupil_dx, pupil_diameter, wavelength, efl, Q=2):
+    """prysm/propagation/dft.py:120-152."""
+    m = math.ceil(Q * pupil_diameter / pupil_dx)
+    return wavelength * efl / pupil_dx / m, m
+
+
+def focus_dft(w, ex):
+    """prysm/propagation/dft.py:297-313."""
+    return ex(w)
+
+
+def unfocus_dft(w, ex):
+    """prysm/propagation/dft.py:335-351."""
+    return ex.adjoint(w)
+
+
+# --------------------------------------------------------------------------------------
+# psf -> otf reductions  (prysm/otf.py:11-202), mode sum, centroid
+# --------------------------------------------------------------------------------------
+
+
+def transform_psf(psf, dx):
+    """fftshift(fft2(ifftshift(psf))), df = 1000/(rows*dx).  prysm/otf.py:28-33."""
+    data = sfft.fftshift(sfft.fft2(sfft.ifftshift(psf)))
+    return data, 1000 / (data.shape[0] * dx)
+
+
+def normalized_transform(psf, dx):
+    """Divide by the sample at floor(s/2).  prysm/otf.py:11-13, 62-74."""
+    data, df = transform_psf(psf, dx)
+    cy, cx = (int(np.floor(s / 2)) for s in data.shape)
+    return data / data[cy, cx], data, df
+
+
+def mtf_from_psf(psf, dx):
+    """prysm/otf.py:77-104."""
+    n, _, df = normalized_transform(psf, dx)
+    return abs(n), df
+
+
+def ptf_from_psf(psf, dx):
+    """prysm/otf.py:107-137."""
+    n, _, df = normalized_transform(psf, dx)
+    return np.angle(n), df
+
+
+def otf_from_psf(psf, dx):
+    """prysm/otf.py:140-167."""
+    n, _, df = normalized_transform(psf, dx)
+    return n, df
+
+
+def sum_of_2d_modes(modes, weights):
+    """tensordot over the leading axis.  prysm/polynomials/fitting.py:7-37."""
+    modes = np.asarray(modes)
+    weights = np.asarray(weights).astype(modes.dtype)
+    return np.tensordot(modes, weights, axes=(0, 0))
+
+
+def centroid(data, dx=None, unit='spatial'):
+    """Centre of mass; spatial = dx*(com - shape//2).  prysm/psf.py:174-203
+    (scipy.ndimage.center_of_mass = sum(data*index)/sum(data) per axis)."""
+    tot = data.sum()
+    idx = np.indices(data.shape)
+    com = tuple(float((data * g).sum() / tot) for g in idx)
+    if unit != 'spatial':
+        return com
+    return tuple(dx * (c - s // 2) for c, s in zip(com, data.shape))
+
+
+# --------------------------------------------------------------------------------------
+# seeded synthetic pupil of SURVEY.md section 8(d)  (input generation; not on the hot path)
+# --------------------------------------------------------------------------------------
+
+
+def noll_to_nm(j):
+    """Noll index -> (n, m), sign convention of prysm/polynomials/zernike.py:653-681
+    (odd j -> negative m i.e. sine term)."""
+    n = int(math.ceil((-1 + math.sqrt(1 + 8 * j)) / 2) - 1)
+    if n == 0:
+        return 0, 0
+    k = j - (n * (n + 1)) // 2 - 1            # position within the order
+    # order n holds |m| = n%2, then each following value twice, up to n
+    seq = [n % 2] if n % 2 == 0 else [1, 1]
+    while len(seq) < n + 1:
+        seq += [seq[-1] + 2] * 2
+    m_abs = seq[k]
+    return n, (-m_abs if j % 2 else m_abs)
+
+
+def zernike_nm(n, m, rho, theta):
+    """Orthonormal (unit-RMS) Zernike: R_n^|m|(rho) * {cos, sin}(|m| theta) * norm,
+    norm = sqrt(2(n+1)/(1+delta_m0)).  prysm/polynomials/zernike.py:25-27, 35-71."""
+    am = abs(m)
+    R = np.zeros_like(rho)
+    for s in range((n - am) // 2 + 1):
+        c = ((-1) ** s * math.factorial(n - s)
+             / (math.factorial(s) * math.factorial((n + am) // 2 - s) * math.factorial((n - am) // 2 - s)))
+        R = R + c * rho ** (n - 2 * s)
+    if m < 0:
+        R = R * np.sin(am * theta)
+    elif m > 0:
+        R = R * np.cos(am * theta)
+    return R * math.sqrt(2 * (n + 1) / (2 if m == 0 else 1))
+
+
+def synthetic_pupil(N, rdtype=np.float32, seed=20260923, sigma_nm=30.0, diameter=10.0, nmodes=36):
+    """SURVEY.md section 8(d) builder: circular aperture of `diameter` mm on an N x N grid
+    (dx = diameter/N, prysm/coordinates.py:344-378), OPD = sum of Noll 2..nmodes+1 orthonormal
+    Zernikes with seeded N(0, sigma) nm coefficients.  Returns amp(bool), opd(rdtype, nm), dx."""
+    dx = diameter / N
+    g = fftrange(N, np.float64) * dx
+    x, y = np.meshgrid(g, g)
+    r = np.sqrt(x * x + y * y)                # prysm/coordinates.py cart_to_polar
+    t = np.arctan2(y, x)
+    amp = (r - diameter / 2) <= 0             # prysm/geometry.py:356-372
+    rho = r / (diameter / 2)
+    coefs = np.random.default_rng(seed).normal(0, sigma_nm, nmodes)
+    opd = np.zeros((N, N))
+    for j, c in zip(range(2, 2 + nmodes), coefs):
+        n, m = noll_to_nm(j)
+        opd += c * zernike_nm(n, m, rho, t)
+    return amp, opd.astype(rdtype), dx
