@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: 2048x2048 pupil -> PSF propagations/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE configs[1], SURVEY.md 8d "C2"): one unit = `Wavefront.focus(efl, Q=2)` of a
+2048^2 complex64 Zernike-aberrated pupil -> 4096^2 complex64 field.  One step = one pass over a
+batch of BATCH distinct pupils resident in HBM (BATCH*32 MiB of inputs >> 126 MB L2, outputs into
+a ring of 4096^2 buffers), so no step can be served from cache.  Multi-GPU = independent replicas
+with disjoint batches (weak scaling, no collective on the data path).
+
+The JSON line carries: value (device-resident throughput, CUDA events, max over ranks), e2e (same
+metric through the public API with pinned HOST buffers, H2D + D2H inside the timed region),
+roofline (algorithmic bytes / measured duration vs the measured HBM peak), cpu_baseline (the
+oracle port = the reference's numpy/scipy algorithm, timed on this box's host cores), clocks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N = 2048
+Q = 2
+K = N * Q
+HENE = 0.6328
+EFL = 100.0
+BATCH = 16                       # pupils per step (16 x 32 MiB = 512 MiB of distinct inputs)
+OUT_RING = 4                     # 4 x 128 MiB output buffers
+ALG_BYTES = 8 * N * N + 8 * K * K  # read pupil + write field = 167 772 160 B / propagation
+METRIC = '2048x2048 pupil->PSF propagations/sec'
+
+
+def oracle():
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import prysm_oracle as O
+    return O
+
+
+def make_pupils(count, seed0=20260923):
+    """Seeded complex64 pupils: the SURVEY 8(d) aperture with per-pupil Zernike coefficients."""
+    import numpy as np
+    O = oracle()
+    amp, opd, dx = O.synthetic_pupil(N, np.float32)
+    base = O.from_amp_and_phase(amp, opd.astype(np.float64), HENE).astype(np.complex64)
+    out = []
+    rng = np.random.default_rng(seed0)
+    for i in range(count):
+        # distinct inputs: a per-pupil global piston + tilt keeps |P| in {0,1} and costs nothing to build
+        ph = rng.uniform(0, 2 * np.pi)
+        tilt = rng.uniform(-3, 3, 2)
+        g = np.arange(N, dtype=np.float32) / N
+        mod = np.exp(1j * (ph + 2 * np.pi * (tilt[0] * g[:, None] + tilt[1] * g[None, :]))).astype(np.complex64)
+        out.append(base * mod)
+    return out, dx
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {'sm_mhz': med, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_focus_rate(seconds_budget, workers, pupils):
+    """Time the oracle port of Wavefront.focus(Q=2) on complex64 2048^2 pupils with scipy.fft workers."""
+    import numpy as np
+    from scipy import fft as sfft
+    O = oracle()
+    done, t_total = 0, 0.0
+    with sfft.set_workers(workers):
+        O.focus(pupils[0], Q)  # warm-up (plan caches, page faults)
+        t_end = time.perf_counter() + seconds_budget
+        while True:
+            t0 = time.perf_counter()
+            out = O.focus(pupils[done % len(pupils)], Q)
+            t_total += time.perf_counter() - t0
+            done += 1
+            if time.perf_counter() > t_end and done >= 3:
+                break
+    assert out.dtype == np.complex64 and out.shape == (K, K)
+    return done / t_total, done, t_total
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm (oracle port: numpy + scipy.fft pocketfft, the same
+    third-party FFT the reference calls) on this box's host cores, all threads, same config/metric."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import numpy as np
+    from scipy import fft as sfft
+    O = oracle()
+    cores = os.cpu_count() or 1
+    per_step = 2                                   # bounded sample: 2 propagations per step
+    pupils, _ = make_pupils(2)
+    with sfft.set_workers(cores):
+        for _ in range(max(1, args.warmup)):
+            O.focus(pupils[0], Q)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            for i in range(per_step):
+                out = O.focus(pupils[i % len(pupils)], Q)
+        dt = time.perf_counter() - t0
+    assert out.dtype == np.complex64
+    value = args.steps * per_step / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'propagations/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'complex64',
+        'data': 'synthetic',
+        'config': {'workload': 'C2: 2048x2048 complex64 pupil -> Wavefront.focus(Q=2) -> 4096x4096 field',
+                   'propagations_per_step': per_step, 'host_threads': cores},
+        'cpu_baseline': {'value': value, 'unit': 'propagations/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{args.steps * per_step} propagations, scipy.fft workers={cores}'},
+        'e2e': {'value': value, 'unit': 'propagations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    import prysm_b200 as pb
+    from prysm_b200 import propagation as P, _ops
+    pb.config.precision = 32
+
+    # ---- synthetic inputs: BATCH distinct pupils per rank, resident in HBM before timing
+    host_pupils, dx = make_pupils(2, seed0=20260923 + rank)
+    base = [torch.from_numpy(p).to(dev) for p in host_pupils]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pupils = []
+    for i in range(BATCH):  # distinct unit-modulus piston per pupil (built once, outside timing)
+        ph = torch.rand((), generator=gen, device=dev) * 6.2831853
+        pupils.append((base[i % 2] * torch.polar(torch.ones((), device=dev), ph)).contiguous())
+    outs = [torch.empty((K, K), dtype=torch.complex64, device=dev) for _ in range(OUT_RING)]
+    scale = 1.0 / K
+    torch.cuda.synchronize()
+
+    def step():
+        for i in range(BATCH):
+            _ops.fft2(pupils[i], (K, K), dir=-1, scale=scale, shift_in=True, shift_out=True, out=outs[i % OUT_RING])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _ops.launch_count(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _ops.launch_count(dev) - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    props = args.steps * BATCH
+    value = world * props / (ms_max * 1e-3)
+
+    # ---- e2e: public API, pinned host buffers in, pinned host buffers out, copies inside the timed region
+    e2e_props = 8
+    hin = [torch.from_numpy(host_pupils[i % 2]).pin_memory() for i in range(2)]
+    hout = [torch.empty((K, K), dtype=torch.complex64).pin_memory() for _ in range(2)]
+    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+
+    def e2e_pass(n):
+        for i in range(n):
+            s = streams[i % 2]
+            with torch.cuda.stream(s):  # double-buffered: copy-in, propagate, copy-out per stream
+                d = hin[i % 2].to(dev, non_blocking=True)
+                wf = P.Wavefront(d, HENE, dx).focus(EFL, Q=Q)
+                hout[i % 2].copy_(wf.data, non_blocking=True)
+        for s in streams:
+            s.synchronize()
+
+    e2e_pass(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_pass(e2e_props)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    t2 = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_props / float(t2.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'MEASURED_PEAKS.json hbm_gbs (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+        t_prop = ms_max * 1e-3 / props
+        achieved = ALG_BYTES / t_prop / 1e9
+        cpu = None
+        if world == 1:
+            cores = os.cpu_count() or 1
+            rate, n_done, secs = cpu_focus_rate(12.0, cores, host_pupils)
+            cpu = {'value': rate, 'unit': 'propagations/s', 'cores': cores, 'kind': 'port',
+                   'sample': f'{n_done} propagations of the same workload in {secs:.1f} s, scipy.fft workers={cores}'}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'propagations/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'complex64', 'data': 'synthetic',
+            'config': {'workload': 'C2: 2048x2048 complex64 pupil -> Wavefront.focus(Q=2) -> 4096x4096 field',
+                       'propagations_per_step': BATCH, 'parallelism': f'replicas x{world}',
+                       'l2_policy': f'{BATCH} distinct 32 MiB inputs + {OUT_RING} x 128 MiB output ring per step (>> 126 MB L2)'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_propagation': ALG_BYTES,
+                         'kernel': 'fused focus pipeline (all passes of one propagation), per GPU',
+                         'us_per_propagation': t_prop * 1e6},
+            'e2e': {'value': e2e_value, 'unit': 'propagations/s', 'h2d_bytes_per_step': 8 * N * N,
+                    'd2h_bytes_per_step': 8 * K * K,
+                    'note': 'per propagation: pinned host pupil in, 4096^2 complex64 field back to pinned host memory'},
+            'gpu_launches': launches,
+            'clocks': clocks,
+        }
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,175 @@
+/*
+ * prysm_b200.h -- C ABI of the B200-native propagation engine (libprysm_b200.so).
+ *
+ * This is the drop-in boundary for the prysm hot path (prysm.propagation + prysm.fttools +
+ * the psf/otf reductions, reference v0.22).  The reference has no FFI of its own: its plug-in
+ * surface is the Python module shim in prysm/mathops.py:11-116.  Each entry point below
+ * states the reference call it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All array pointers are DEVICE pointers owned
+ *     by the caller (row-major, index order [y][x], interleaved complex) unless a parameter is
+ *     documented as "host".  The library owns only the opaque handle (twiddle tables, scratch).
+ *   - Every call is asynchronous on the `stream` argument (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream).  A handle is bound to one device and is not thread-safe.
+ *   - Return value: PB_OK (0) or a negative pb_status; pb_last_error(h) gives the message.
+ *     Nothing throws or exits across this boundary.  There is no CPU fallback.
+ *   - dtype selects the working precision like prysm.conf.config.precision
+ *     (prysm/conf.py:28-96): PB_C64 = complex64 fields / float32 reals, PB_C128 = complex128 /
+ *     float64.
+ */
+#ifndef PRYSM_B200_H
+#define PRYSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_handle_s* pb_handle_t;
+
+typedef enum { PB_C64 = 0, PB_C128 = 1 } pb_dtype;
+
+typedef enum {
+    PB_OK = 0,
+    PB_ERR_INVALID = -1,      /* bad argument */
+    PB_ERR_UNSUPPORTED = -2,  /* shape / length outside what the kernels cover */
+    PB_ERR_CUDA = -3,         /* CUDA runtime error (message has the cudaError string) */
+    PB_ERR_ALLOC = -4
+} pb_status;
+
+/* how the input field of pb_fft2 is presented */
+typedef enum {
+    PB_IN_COMPLEX = 0,  /* in = complex (ny, nx) */
+    PB_IN_REAL = 1,     /* in = real (ny, nx), imaginary part 0 (prysm/otf.py:31 takes a real PSF) */
+    PB_IN_AMP_OPD = 2   /* field = amp * exp(i*kscale*opd): prysm/propagation/wavefront.py:59-79 fused in */
+} pb_in_kind;
+
+typedef enum { PB_AMP_NONE = 0, PB_AMP_REAL = 1, PB_AMP_U8 = 2 } pb_amp_kind;
+
+typedef enum {
+    PB_OUT_COMPLEX = 0,    /* complex field */
+    PB_OUT_INTENSITY = 1,  /* re^2+im^2 (prysm/propagation/wavefront.py:147-151) into a real array */
+    PB_OUT_ACCUMULATE = 2  /* out += weight*(re^2+im^2): the per-wavelength term of
+                              prysm/polynomials/fitting.py:37 applied as it is produced */
+} pb_out_kind;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int pb_create(pb_handle_t* out, int device);
+int pb_destroy(pb_handle_t h);
+const char* pb_last_error(pb_handle_t h);
+const char* pb_version(void);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+long long pb_launch_count(pb_handle_t h);
+
+/* ---- centred / plain 2-D FFT with fused pad, shifts, synthesis and |.|^2 ---------------
+ * out = crop( S_out( FFT2_{dir}( S_in( pad( field ) ) ) ) ) * scale
+ *   field : (ny, nx), see pb_in_kind; row pitch in_ld elements
+ *   pad   : centred zero pad to (ky, kx) with the pad2d offset rule ceil((k-n)/2)
+ *           (prysm/fttools.py:43-100)
+ *   S_in  : ifftshift if shift_in, S_out: fftshift if shift_out (all axes)
+ *   dir   : -1 forward (exp(-i..)), +1 inverse; scale is applied by the caller's norm rule
+ *           (ortho: 1/sqrt(ky*kx); numpy default: 1 forward, 1/(ky*kx) inverse)
+ *   crop  : centred (oy, ox) window with the crop_center rule (prysm/fttools.py:103-125)
+ * Replaces: propagation.focus / unfocus and their adjoints (prysm/propagation/fft.py:7-85),
+ *           fft.fft2 / ifft2 call sites (prysm/otf.py:31,59), Wavefront.from_amp_and_phase +
+ *           .focus + .intensity chains (prysm/propagation/wavefront.py:59-79,147-151,478-504).
+ * Any ky, kx >= 1 is accepted (non powers of two run Bluestein on the same kernels). */
+int pb_fft2(pb_handle_t h, int dtype,
+            const void* in, int in_kind, const void* amp, int amp_kind, double kscale,
+            int ny, int nx, long long in_ld,
+            int ky, int kx, int dir, double scale, int shift_in, int shift_out,
+            void* out, int out_kind, double weight, int oy, int ox, long long out_ld,
+            void* stream);
+
+/* ---- 1-D FFT along one axis of a 2-D array, numpy fft(a, n, axis) semantics ------------
+ * Zero-extends or truncates to n along `axis` (0 = y/columns, 1 = x/rows).
+ * Replaces fft.fft / fft.ifft call sites in prysm/fttools.py:301-321, 519-533. */
+int pb_fft1(pb_handle_t h, int dtype, const void* in, int ny, int nx, long long in_ld,
+            int axis, int n, int dir, double scale, void* out, long long out_ld, void* stream);
+
+/* ---- the same, with fused multipliers and an output window -----------------------------
+ * For every line b along `axis`:  u[j] = in_line[j] * pre_e[j] * pre_b[b]   (j < n_line, zero-extended to n)
+ *                                 U = DFT_n(u);   out_line[q] = U[q + out_off] * post_e[q] * post_b[b] * scale
+ * for q in [0, n_out).  Any multiplier may be NULL; *_conj conjugates it.  pre_e has n_line
+ * entries, post_e has n_out entries, pre_b / post_b have one entry per line.
+ * One call is one Bluestein half-step of CZT (prysm/fttools.py:298-324) or one FFTDFT axis
+ * (prysm/fttools.py:443-459) with the chirp / ramp multiplies and the slice fused in. */
+int pb_axis_dft(pb_handle_t h, int dtype, const void* in, int ny, int nx, long long in_ld, int axis,
+                int n, int dir, double scale,
+                const void* pre_e, int pre_e_conj, const void* pre_b, int pre_b_conj,
+                const void* post_e, int post_e_conj, const void* post_b, int post_b_conj,
+                int out_off, int n_out, void* out, long long out_ld, void* stream);
+
+/* ---- angular spectrum ------------------------------------------------------------------
+ * out(ky,kx) = ifft2( fft2( pad(in -> ky,kx) ) * TF ), TF = outer(ty, tx) when tf == NULL,
+ * else the full (ky,kx) array tf; conj_tf applies conj(TF) (adjoint); the result is cropped to
+ * (oy, ox) with the crop_center rule (forward: oy=ky, ox=kx i.e. stays padded).
+ * Replaces prysm/propagation/angular_spectrum.py:9-79. */
+int pb_angular_spectrum(pb_handle_t h, int dtype, const void* in, int ny, int nx,
+                        int ky, int kx, const void* ty, const void* tx, const void* tf,
+                        int conj_tf, void* out, int oy, int ox, void* stream);
+
+/* the two separable factors exp(-i*pi*wvl_mm*z*k^2), k = fftfreq(n, dx) rounded to the working
+ * precision first (prysm/propagation/angular_spectrum.py:102-113).  ty: ky values, tx: kx. */
+int pb_angular_spectrum_vectors(pb_handle_t h, int dtype, int ky, int kx, double wvl_um,
+                                double dx_mm, double z_mm, void* ty, void* tx, void* stream);
+
+/* ---- matrix DFT ------------------------------------------------------------------------
+ * basis E[j,l] = exp(sign*2*pi*i*f[j]*x[l]), (m, n) complex.  f, x: HOST double arrays.
+ * The phase is formed and range-reduced in fp64 before the sincos.  prysm/fttools.py:187-191 */
+int pb_mdft_basis(pb_handle_t h, int dtype, const double* f_host, int m, const double* x_host,
+                  int n, int sign, void* E, void* stream);
+
+/* C(m,n) = alpha * opA(A) * opB(B); op: 0 = as is, 1 = transpose, 2 = conjugate transpose,
+ * 3 = conjugate.  A is (m,k) after op, B is (k,n) after op.  Complex, row-major.
+ * Replaces the `@` chains of MDFT.__call__ / adjoint (prysm/fttools.py:201-228). */
+int pb_cgemm(pb_handle_t h, int dtype, int opA, int opB, int m, int n, int k, double alpha,
+             const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
+             void* stream);
+
+/* out(my,mx) = norm * Ey(my,ny) @ a(ny,nx) @ Ex(mx,nx)^T   (adjoint = 0), or
+ * out(ny,nx) = norm * Ey^H @ g(my,mx) @ conj(Ex)            (adjoint = 1),
+ * association order chosen by left_first (prysm/fttools.py:198-228).  `work` is caller scratch
+ * of at least pb_mdft_work_elems(...) complex elements. */
+int pb_mdft_apply(pb_handle_t h, int dtype, const void* Ey, const void* Ex, int my, int ny,
+                  int mx, int nx, const void* a, void* out, double norm, int adjoint,
+                  int left_first, void* work, void* stream);
+long long pb_mdft_work_elems(int my, int ny, int mx, int nx, int adjoint, int left_first);
+
+/* ---- elementwise / reductions -----------------------------------------------------------
+ * out = amp * exp(i*kscale*opd)   (amp optional).  prysm/propagation/wavefront.py:59-96 */
+int pb_phase_screen(pb_handle_t h, int dtype, const void* amp, int amp_kind, const void* opd,
+                    double kscale, long long count, void* out, void* stream);
+/* out (+)= weight * |in|^2.  prysm/propagation/wavefront.py:147-151 */
+int pb_intensity(pb_handle_t h, int dtype, const void* in, long long count, double weight,
+                 int accumulate, void* out, void* stream);
+/* out = a (op) b elementwise on complex arrays; b == NULL uses the scalar (s_re, s_im) instead;
+ * reverse swaps the operands.  op: 0 mul, 1 div, 2 add, 3 sub.
+ * Wavefront.__numerical_operation__ (prysm/propagation/wavefront.py:360-411). */
+int pb_binary(pb_handle_t h, int dtype, int op, const void* a, const void* b, double s_re,
+              double s_im, int reverse, long long count, void* out, void* stream);
+/* out[y,x] = in[y,x] * vy[y] * vx[x] * scale (either vector may be NULL; conj flags per vector).
+ * The chirp / phase-ramp multiplies of CZT and FFTDFT (prysm/fttools.py:298-324, 443-459). */
+int pb_mul_outer(pb_handle_t h, int dtype, const void* in, long long in_ld, int ny, int nx,
+                 const void* vy, int conj_y, const void* vx, int conj_x, double scale, void* out,
+                 long long out_ld, void* stream);
+/* out(n) = sum_k weights[k] * modes[k][n]; weights: HOST doubles.  prysm/polynomials/fitting.py:37 */
+int pb_weighted_sum(pb_handle_t h, int dtype, const void* modes, int k, long long count,
+                    const double* weights_host, void* out, void* stream);
+/* centre-normalised transfer functions from the complex transform D (ny,nx):
+ * n = D / D[ny/2, nx/2]; which bit0 -> mtf=|n| (real), bit1 -> ptf=angle(n) (real), bit2 -> otf=n.
+ * prysm/otf.py:62-202 */
+int pb_otf_normalize(pb_handle_t h, int dtype, const void* D, int ny, int nx, int which,
+                     void* mtf, void* ptf, void* otf, void* stream);
+/* moments of a real array: sums_host[0..2] = sum(d), sum(d*y), sum(d*x) (HOST doubles; this call
+ * synchronises the stream).  prysm/psf.py:174-203 */
+int pb_moments(pb_handle_t h, int dtype, const void* data, int ny, int nx, double* sums_host,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRYSM_B200_H */

@@ -1,0 +1,114 @@
+"""ctypes binding of libprysm_b200.so (the C ABI declared in include/prysm_b200.h).
+
+The library is dlopen'ed directly -- no pybind / torch-extension layer.  If it is missing the
+import fails loudly: there is no CPU or PyTorch fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_lib', 'libprysm_b200.so')
+
+PB_C64, PB_C128 = 0, 1
+IN_COMPLEX, IN_REAL, IN_AMP_OPD = 0, 1, 2
+AMP_NONE, AMP_REAL, AMP_U8 = 0, 1, 2
+OUT_COMPLEX, OUT_INTENSITY, OUT_ACCUMULATE = 0, 1, 2
+OP_N, OP_T, OP_H, OP_C = 0, 1, 2, 3
+
+_vp, _i, _ll, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_double
+
+# name -> (restype, argtypes); must list every symbol of include/prysm_b200.h
+SIGNATURES = {
+    'pb_create': (_i, [C.POINTER(_vp), _i]),
+    'pb_destroy': (_i, [_vp]),
+    'pb_last_error': (C.c_char_p, [_vp]),
+    'pb_version': (C.c_char_p, []),
+    'pb_launch_count': (_ll, [_vp]),
+    'pb_fft2': (_i, [_vp, _i, _vp, _i, _vp, _i, _d, _i, _i, _ll, _i, _i, _i, _d, _i, _i,
+                     _vp, _i, _d, _i, _i, _ll, _vp]),
+    'pb_fft1': (_i, [_vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _d, _vp, _ll, _vp]),
+    'pb_axis_dft': (_i, [_vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _d, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _ll, _vp]),
+    'pb_angular_spectrum': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    'pb_angular_spectrum_vectors': (_i, [_vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp]),
+    'pb_mdft_basis': (_i, [_vp, _i, C.POINTER(_d), _i, C.POINTER(_d), _i, _i, _vp, _vp]),
+    'pb_cgemm': (_i, [_vp, _i, _i, _i, _i, _i, _i, _d, _vp, _ll, _vp, _ll, _vp, _ll, _vp]),
+    'pb_mdft_apply': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _d, _i, _i, _vp, _vp]),
+    'pb_mdft_work_elems': (_ll, [_i, _i, _i, _i, _i, _i]),
+    'pb_phase_screen': (_i, [_vp, _i, _vp, _i, _vp, _d, _ll, _vp, _vp]),
+    'pb_intensity': (_i, [_vp, _i, _vp, _ll, _d, _i, _vp, _vp]),
+    'pb_binary': (_i, [_vp, _i, _i, _vp, _vp, _d, _d, _i, _ll, _vp, _vp]),
+    'pb_mul_outer': (_i, [_vp, _i, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _d, _vp, _ll, _vp]),
+    'pb_weighted_sum': (_i, [_vp, _i, _vp, _i, _ll, C.POINTER(_d), _vp, _vp]),
+    'pb_otf_normalize': (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'pb_moments': (_i, [_vp, _i, _vp, _i, _i, C.POINTER(_d), _vp]),
+}
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise ImportError(
+            f'{path} is missing: build it with `python -m prysm_b200.build` '
+            '(prysm_b200 has no CPU fallback)')
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so and the header diverge
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = load_library()
+
+
+class B200Error(RuntimeError):
+    """A libprysm_b200 call failed (CUDA error, unsupported shape, bad argument)."""
+
+
+class Handle:
+    """One engine handle per CUDA device (twiddle tables + scratch live here)."""
+
+    def __init__(self, device):
+        self._h = _vp()
+        rc = lib.pb_create(C.byref(self._h), int(device))
+        if rc != 0:
+            raise B200Error(f'pb_create(device={device}) failed with status {rc}: is a CUDA device visible?')
+        self.device = int(device)
+
+    def check(self, rc):
+        if rc != 0:
+            msg = lib.pb_last_error(self._h).decode()
+            if rc == -1:
+                raise ValueError(msg)
+            raise B200Error(f'status {rc}: {msg}')
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def launch_count(self):
+        return int(lib.pb_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib.pb_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_handles = {}
+
+
+def handle_for(device_index):
+    h = _handles.get(device_index)
+    if h is None:
+        h = _handles[device_index] = Handle(device_index)
+    return h
+
+
+def version():
+    return lib.pb_version().decode()

@@ -1,0 +1,321 @@
+"""Thin tensor-level wrappers over the C ABI: each function takes CUDA torch tensors (or host
+arrays, which are uploaded), allocates the output with torch's caching allocator and makes
+exactly one library call on torch's current stream.  PyTorch is plumbing here (device memory,
+streams); every kernel is in libprysm_b200.so.
+"""
+import math
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from ._capi import lib
+
+_REAL_OF = {torch.complex64: torch.float32, torch.complex128: torch.float64}
+_CPLX_OF = {torch.float32: torch.complex64, torch.float64: torch.complex128}
+_CODE = {torch.complex64: capi.PB_C64, torch.complex128: capi.PB_C128,
+         torch.float32: capi.PB_C64, torch.float64: capi.PB_C128}
+
+_default_device = None
+
+
+def set_device(device=None):
+    """Select the CUDA device new arrays are placed on (default: torch's current device)."""
+    global _default_device
+    _default_device = None if device is None else torch.device(device)
+
+
+def device():
+    if _default_device is not None:
+        return _default_device
+    if not torch.cuda.is_available():
+        raise capi.B200Error('no CUDA device is visible: prysm_b200 has no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def torch_dtype(np_or_torch_dtype):
+    if isinstance(np_or_torch_dtype, torch.dtype):
+        return np_or_torch_dtype
+    return {np.dtype('float32'): torch.float32, np.dtype('float64'): torch.float64,
+            np.dtype('complex64'): torch.complex64, np.dtype('complex128'): torch.complex128,
+            np.dtype('bool'): torch.bool, np.dtype('uint8'): torch.uint8,
+            np.dtype('int64'): torch.int64, np.dtype('int32'): torch.int32}[np.dtype(np_or_torch_dtype)]
+
+
+def asdevice(a, dtype=None):
+    """Host array / scalar sequence / tensor -> contiguous CUDA tensor (no copy if already one)."""
+    if isinstance(a, torch.Tensor):
+        t = a if a.is_cuda else a.to(device(), non_blocking=True)
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(a)).to(device(), non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def asnumpy(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def ascomplex(t):
+    """Promote a real / bool tensor to the complex dtype of matching precision."""
+    if t.is_complex():
+        return t
+    if t.dtype == torch.float64:
+        return t.to(torch.complex128)
+    return t.to(torch.complex64)
+
+
+def _ctx(t):
+    h = capi.handle_for(t.device.index)
+    return h, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _darr(v):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    return v, v.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# ------------------------------------------------------------------------------------------
+def fft2(field, k=None, *, dir=-1, scale=1.0, shift_in=False, shift_out=False, crop=None,
+         out_kind=capi.OUT_COMPLEX, weight=1.0, out=None, amp=None, opd=None, kscale=0.0):
+    """pb_fft2.  Either `field` (complex or real 2-D tensor) or (amp, opd, kscale)."""
+    if opd is not None:
+        src = opd
+        in_kind = capi.IN_AMP_OPD
+        if amp is None:
+            amp_kind, amp_t = capi.AMP_NONE, None
+        elif amp.dtype in (torch.bool, torch.uint8):
+            amp_kind, amp_t = capi.AMP_U8, amp.contiguous()
+        else:
+            amp_kind, amp_t = capi.AMP_REAL, amp.to(opd.dtype).contiguous()
+        cdtype = _CPLX_OF[opd.dtype]
+    else:
+        src = field
+        amp_kind, amp_t = capi.AMP_NONE, None
+        if field.is_complex():
+            in_kind, cdtype = capi.IN_COMPLEX, field.dtype
+        else:
+            if field.dtype not in _CPLX_OF:
+                src = field.to(torch.float32)
+            in_kind, cdtype = capi.IN_REAL, _CPLX_OF[src.dtype]
+    src = src.contiguous()
+    ny, nx = src.shape
+    ky, kx = (ny, nx) if k is None else k
+    oy, ox = (ky, kx) if crop is None else crop
+    if out is None:
+        odt = cdtype if out_kind == capi.OUT_COMPLEX else _REAL_OF[cdtype]
+        if out_kind == capi.OUT_ACCUMULATE:
+            raise ValueError('accumulate needs an existing `out` array')
+        out = torch.empty((oy, ox), dtype=odt, device=src.device)
+    h, st = _ctx(src)
+    h.check(lib.pb_fft2(h.ptr, _CODE[cdtype], _p(src), in_kind, _p(amp_t), amp_kind, float(kscale),
+                        ny, nx, nx, ky, kx, int(dir), float(scale), int(shift_in), int(shift_out),
+                        _p(out), out_kind, float(weight), oy, ox, out.stride(0), st))
+    return out
+
+
+def fft1(a, n=None, axis=-1, dir=-1, scale=1.0):
+    """pb_fft1: numpy fft(a, n, axis) on a 2-D complex tensor."""
+    a = ascomplex(a).contiguous()
+    ny, nx = a.shape
+    axis = axis % 2
+    if n is None:
+        n = a.shape[axis]
+    oshape = (n, nx) if axis == 0 else (ny, n)
+    out = torch.empty(oshape, dtype=a.dtype, device=a.device)
+    h, st = _ctx(a)
+    h.check(lib.pb_fft1(h.ptr, _CODE[a.dtype], _p(a), ny, nx, nx, axis, int(n), int(dir), float(scale),
+                        _p(out), oshape[1], st))
+    return out
+
+
+def axis_dft(a, n, axis, dir=-1, scale=1.0, pre_e=None, pre_e_conj=False, pre_b=None, pre_b_conj=False,
+             post_e=None, post_e_conj=False, post_b=None, post_b_conj=False, out_off=0, n_out=None):
+    """pb_axis_dft: one DFT pass with fused multipliers and an output window."""
+    a = ascomplex(a).contiguous()
+    ny, nx = a.shape
+    axis = axis % 2
+    if n_out is None:
+        n_out = n - out_off
+    oshape = (n_out, nx) if axis == 0 else (ny, n_out)
+    out = torch.empty(oshape, dtype=a.dtype, device=a.device)
+    h, st = _ctx(a)
+    h.check(lib.pb_axis_dft(h.ptr, _CODE[a.dtype], _p(a), ny, nx, nx, axis, int(n), int(dir), float(scale),
+                            _p(pre_e), int(pre_e_conj), _p(pre_b), int(pre_b_conj),
+                            _p(post_e), int(post_e_conj), _p(post_b), int(post_b_conj),
+                            int(out_off), int(n_out), _p(out), oshape[1], st))
+    return out
+
+
+def angular_spectrum(field, k, ty=None, tx=None, tf=None, conj_tf=False, crop=None):
+    field = ascomplex(field).contiguous()
+    ny, nx = field.shape
+    ky, kx = k
+    oy, ox = (ky, kx) if crop is None else crop
+    out = torch.empty((oy, ox), dtype=field.dtype, device=field.device)
+    if tf is not None:
+        tf = tf.to(field.dtype).contiguous()
+    h, st = _ctx(field)
+    h.check(lib.pb_angular_spectrum(h.ptr, _CODE[field.dtype], _p(field), ny, nx, ky, kx, _p(ty), _p(tx), _p(tf),
+                                    int(conj_tf), _p(out), oy, ox, st))
+    return out
+
+
+def angular_spectrum_vectors(shape, wvl, dx, z, cdtype, dev):
+    ky, kx = shape
+    ty = torch.empty(ky, dtype=cdtype, device=dev)
+    tx = torch.empty(kx, dtype=cdtype, device=dev)
+    h, st = _ctx(ty)
+    h.check(lib.pb_angular_spectrum_vectors(h.ptr, _CODE[cdtype], ky, kx, float(wvl), float(dx), float(z),
+                                            _p(ty), _p(tx), st))
+    return ty, tx
+
+
+def mdft_basis(f, x, sign, cdtype, dev):
+    """E[j, l] = exp(sign*2*pi*i*f[j]*x[l]) built on the device from fp64 host coordinates."""
+    f, fp = _darr(f)
+    x, xp = _darr(x)
+    E = torch.empty((len(f), len(x)), dtype=cdtype, device=dev)
+    h, st = _ctx(E)
+    h.check(lib.pb_mdft_basis(h.ptr, _CODE[cdtype], fp, len(f), xp, len(x), int(sign), _p(E), st))
+    return E
+
+
+def cgemm(A, B, opA=capi.OP_N, opB=capi.OP_N, alpha=1.0):
+    m = A.shape[0] if opA in (capi.OP_N, capi.OP_C) else A.shape[1]
+    k = A.shape[1] if opA in (capi.OP_N, capi.OP_C) else A.shape[0]
+    n = B.shape[1] if opB in (capi.OP_N, capi.OP_C) else B.shape[0]
+    kb = B.shape[0] if opB in (capi.OP_N, capi.OP_C) else B.shape[1]
+    if k != kb:
+        raise ValueError(f'matmul: inner dimensions {k} and {kb} differ')
+    A, B = A.contiguous(), B.contiguous()
+    out = torch.empty((m, n), dtype=A.dtype, device=A.device)
+    h, st = _ctx(A)
+    h.check(lib.pb_cgemm(h.ptr, _CODE[A.dtype], opA, opB, m, n, k, float(alpha), _p(A), A.shape[1], _p(B), B.shape[1],
+                         _p(out), n, st))
+    return out
+
+
+def mdft_apply(Ey, Ex, a, norm, adjoint, left_first):
+    my, ny = Ey.shape
+    mx, nx = Ex.shape
+    a = a.contiguous()
+    want = (my, mx) if adjoint else (ny, nx)
+    if tuple(a.shape) != want:
+        raise ValueError(f'array of shape {tuple(a.shape)} does not match the executor ({want})')
+    oshape = (ny, nx) if adjoint else (my, mx)
+    out = torch.empty(oshape, dtype=a.dtype, device=a.device)
+    nwork = lib.pb_mdft_work_elems(my, ny, mx, nx, int(adjoint), int(left_first))
+    work = torch.empty(nwork, dtype=a.dtype, device=a.device)
+    h, st = _ctx(a)
+    h.check(lib.pb_mdft_apply(h.ptr, _CODE[a.dtype], _p(Ey), _p(Ex), my, ny, mx, nx, _p(a), _p(out), float(norm),
+                              int(adjoint), int(left_first), _p(work), st))
+    return out
+
+
+def phase_screen(amp, opd, kscale):
+    opd = opd.contiguous()
+    if opd.dtype not in _CPLX_OF:
+        opd = opd.to(torch.float32)
+    if amp is None:
+        amp_kind, amp_t = capi.AMP_NONE, None
+    elif amp.dtype in (torch.bool, torch.uint8):
+        amp_kind, amp_t = capi.AMP_U8, amp.contiguous()
+    else:
+        amp_kind, amp_t = capi.AMP_REAL, amp.to(opd.dtype).contiguous()
+    out = torch.empty(opd.shape, dtype=_CPLX_OF[opd.dtype], device=opd.device)
+    h, st = _ctx(opd)
+    h.check(lib.pb_phase_screen(h.ptr, _CODE[opd.dtype], _p(amp_t), amp_kind, _p(opd), float(kscale), opd.numel(),
+                                _p(out), st))
+    return out
+
+
+def intensity(field, weight=1.0, out=None):
+    field = field.contiguous()
+    acc = out is not None
+    if out is None:
+        out = torch.empty(field.shape, dtype=_REAL_OF[field.dtype], device=field.device)
+    h, st = _ctx(field)
+    h.check(lib.pb_intensity(h.ptr, _CODE[field.dtype], _p(field), field.numel(), float(weight), int(acc), _p(out), st))
+    return out
+
+
+_BINOPS = {'mul': 0, 'truediv': 1, 'add': 2, 'sub': 3}
+
+
+def binary(op, a, b, reverse=False):
+    """a (op) b for complex tensor a and tensor-or-scalar b (pb_binary)."""
+    a = a.contiguous()
+    if isinstance(b, torch.Tensor):
+        if b.shape != a.shape:
+            raise ValueError(f'shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}')
+        b = b.to(a.dtype).contiguous()
+        s = 0j
+    else:
+        s, b = complex(b), None
+    out = torch.empty_like(a)
+    h, st = _ctx(a)
+    h.check(lib.pb_binary(h.ptr, _CODE[a.dtype], _BINOPS[op], _p(a), _p(b), s.real, s.imag, int(reverse), a.numel(),
+                          _p(out), st))
+    return out
+
+
+def mul_outer(a, vy=None, vx=None, conj_y=False, conj_x=False, scale=1.0, out=None):
+    """a[y, x] * vy[y] * vx[x] * scale; `a` may be a strided (sliced) view with unit column stride."""
+    if a.stride(1) != 1:
+        a = a.contiguous()
+    ny, nx = a.shape
+    if out is None:
+        out = torch.empty((ny, nx), dtype=a.dtype, device=a.device)
+    h, st = _ctx(a)
+    h.check(lib.pb_mul_outer(h.ptr, _CODE[a.dtype], _p(a), a.stride(0), ny, nx, _p(vy), int(conj_y), _p(vx),
+                             int(conj_x), float(scale), _p(out), out.stride(0), st))
+    return out
+
+
+def weighted_sum(modes, weights):
+    modes = modes.contiguous()
+    k = modes.shape[0]
+    w, wp = _darr(weights)
+    out = torch.empty(modes.shape[1:], dtype=modes.dtype, device=modes.device)
+    h, st = _ctx(modes)
+    h.check(lib.pb_weighted_sum(h.ptr, _CODE[modes.dtype], _p(modes), k, out.numel(), wp, _p(out), st))
+    return out
+
+
+def otf_normalize(D, which):
+    D = D.contiguous()
+    ny, nx = D.shape
+    rd = _REAL_OF[D.dtype]
+    mtf = torch.empty((ny, nx), dtype=rd, device=D.device) if which & 1 else None
+    ptf = torch.empty((ny, nx), dtype=rd, device=D.device) if which & 2 else None
+    otf = torch.empty((ny, nx), dtype=D.dtype, device=D.device) if which & 4 else None
+    h, st = _ctx(D)
+    h.check(lib.pb_otf_normalize(h.ptr, _CODE[D.dtype], _p(D), ny, nx, which, _p(mtf), _p(ptf), _p(otf), st))
+    return mtf, ptf, otf
+
+
+def moments(data):
+    data = data.contiguous()
+    if data.dtype not in _CPLX_OF:
+        data = data.to(torch.float32)
+    ny, nx = data.shape
+    sums = (C.c_double * 3)()
+    h, st = _ctx(data)
+    h.check(lib.pb_moments(h.ptr, _CODE[data.dtype], _p(data), ny, nx, sums, st))
+    return sums[0], sums[1], sums[2]
+
+
+def launch_count(dev=None):
+    dev = device() if dev is None else torch.device(dev)
+    return capi.handle_for(dev.index).launch_count()
+
+
+def ceil_half(d):
+    return math.ceil(d / 2)

@@ -1,0 +1,100 @@
+// Shared declarations for libprysm_b200: handle, error plumbing, complex helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../../include/prysm_b200.h"
+
+namespace pb {
+
+template <typename R> struct cplx_of;
+template <> struct cplx_of<float> { using type = float2; };
+template <> struct cplx_of<double> { using type = double2; };
+template <typename R> using cplx = typename cplx_of<R>::type;
+
+template <typename R> __host__ __device__ inline cplx<R> mk(R x, R y) { cplx<R> c; c.x = x; c.y = y; return c; }
+template <typename C> __host__ __device__ inline C cmul(C a, C b) {
+    C c; c.x = a.x * b.x - a.y * b.y; c.y = a.x * b.y + a.y * b.x; return c;
+}
+template <typename C> __host__ __device__ inline C cmulc(C a, C b) {  // a * conj(b)
+    C c; c.x = a.x * b.x + a.y * b.y; c.y = a.y * b.x - a.x * b.y; return c;
+}
+template <typename C> __host__ __device__ inline C cadd(C a, C b) { C c; c.x = a.x + b.x; c.y = a.y + b.y; return c; }
+template <typename C> __host__ __device__ inline C csub(C a, C b) { C c; c.x = a.x - b.x; c.y = a.y - b.y; return c; }
+template <typename C> __host__ __device__ inline C cconj(C a) { a.y = -a.y; return a; }
+
+// exp(2*pi*i*turns) with the argument reduced in fp64 before the sincos.
+__device__ inline float2 expi_turns(double turns, float) {
+    double fr = turns - rint(turns);
+    float s, c; sincospif(2.0f * (float)fr, &s, &c);
+    return make_float2(c, s);
+}
+__device__ inline double2 expi_turns(double turns, double) {
+    double fr = turns - rint(turns);
+    double s, c; sincospi(2.0 * fr, &s, &c);
+    return make_double2(c, s);
+}
+
+struct TwKey {
+    int n; int dtype; int kind;  // kind 0: w_n^k table; 1/2: bluestein chirp (dir -1/+1); 3/4: bluestein filter spectrum
+    bool operator<(const TwKey& o) const {
+        if (n != o.n) return n < o.n;
+        if (dtype != o.dtype) return dtype < o.dtype;
+        return kind < o.kind;
+    }
+};
+
+struct Handle {
+    int device = 0;
+    std::string err;
+    long long launches = 0;
+    std::map<TwKey, void*> tables;
+    // scratch arenas, grown on demand (never on a warmed-up hot call)
+    void* scratch[3] = {nullptr, nullptr, nullptr};
+    size_t scratch_bytes[3] = {0, 0, 0};
+    int sm_count = 148;
+    int max_smem_optin = 0;
+};
+
+inline int fail(Handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define PB_CUDA(h, call)                                                                      \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return pb::fail(h, PB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+#define PB_LAUNCH_CHECK(h)                                                                    \
+    do {                                                                                      \
+        cudaError_t e_ = cudaGetLastError();                                                  \
+        if (e_ != cudaSuccess)                                                                \
+            return pb::fail(h, PB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+        (h)->launches++;                                                                      \
+    } while (0)
+
+#define PB_TRY(expr)               \
+    do {                           \
+        int rc_ = (expr);          \
+        if (rc_ != PB_OK) return rc_; \
+    } while (0)
+
+int ensure_scratch(Handle* h, int slot, size_t bytes, void** out);
+// device table of w_n^k = exp(-2*pi*i*k/n), k in [0,n)
+int get_twiddles(Handle* h, int n, int dtype, const void** out);
+
+inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+inline size_t csize(int dtype) { return dtype == PB_C64 ? 8 : 16; }
+inline size_t rsize(int dtype) { return dtype == PB_C64 ? 4 : 8; }
+
+}  // namespace pb

@@ -1,0 +1,301 @@
+"""Fourier tools on the B200 engine -- same names and semantics as prysm.fttools
+(reference prysm/fttools.py), arrays are CUDA tensors, every transform is a libprysm_b200 call.
+
+Executors (MDFT / CZT / FFTDFT) keep the reference constructor `(x, y, fx, fy, sign, norm)`,
+`__call__`, `.adjoint` and `.nbytes()`; holding an instance is the caching mechanism
+(prysm/fttools.py:181-183).  Coordinates are taken on the host in fp64 and every basis /
+chirp argument is range-reduced in fp64 before the sincos, so the complex64 executors track
+the reference's *fp64* output (the reference's own fp32 chirps are only good to ~1e-4 at
+2048^2).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _ops
+from ._capi import OP_N, OP_T, OP_H, OP_C  # noqa: F401
+from .conf import config
+
+
+def _host(v):
+    """1-D coordinate vector -> host float64."""
+    if isinstance(v, torch.Tensor):
+        v = v.detach().cpu().numpy()
+    return np.asarray(v, dtype=np.float64)
+
+
+def fftrange(n, dtype=None):
+    """FFT-aligned integer grid, zero at index n//2 (prysm/fttools.py:13-15).  Device tensor."""
+    dt = config.real_dtype if dtype is None else _ops.torch_dtype(dtype)
+    return torch.arange(-(n // 2), -(n // 2) + n, dtype=dt, device=_ops.device())
+
+
+def next_fast_len(n):
+    """Next transform length the radix kernels run natively: a power of two
+    (the reference asks its FFT backend, prysm/fttools.py:23-31; any K >= N+M-1 is valid for CZT)."""
+    return 1 << max(0, math.ceil(math.log2(n)))
+
+
+def fftfreq(n, d=1.0):
+    """DFT sample frequencies, numpy ordering, at config.precision (prysm/fttools.py:34-40)."""
+    return _ops.asdevice(np.fft.fftfreq(n, d).astype(config.precision))
+
+
+def forward_ft_unit(dx, samples, shift=True):
+    """prysm/fttools.py:128-152."""
+    u = np.fft.fftfreq(samples, dx).astype(config.precision)
+    return _ops.asdevice(np.fft.fftshift(u) if shift else u)
+
+
+def pad2d(array, Q=2, value=0, mode='constant', out_shape=None):
+    """Centred pad; offsets ceil((out-in)/2) (prysm/fttools.py:43-100).  Q == 1 returns the input."""
+    if Q == 1 and out_shape is None:
+        return array
+    if mode != 'constant':
+        raise NotImplementedError("only mode='constant' is on the propagation path")
+    array = _ops.asdevice(array)
+    in_shape = tuple(array.shape)
+    if out_shape is None:
+        out_shape = [math.ceil(s * Q) for s in in_shape]
+    elif isinstance(out_shape, int):
+        out_shape = [out_shape] * array.ndim
+    offs = [math.ceil((o - i) / 2) for o, i in zip(out_shape, in_shape)]
+    if value != 0:
+        out = torch.full(tuple(out_shape), value, dtype=array.dtype, device=array.device)
+    else:
+        out = torch.zeros(tuple(out_shape), dtype=array.dtype, device=array.device)
+    view = out[offs[0]:offs[0] + in_shape[0], offs[1]:offs[1] + in_shape[1]]
+    if array.is_complex():
+        _ops.mul_outer(array, out=view)
+    else:
+        view.copy_(array)
+    return out
+
+
+def crop_center(img, out_shape):
+    """Centred window starting at ceil((in-out)/2): a view (prysm/fttools.py:103-125)."""
+    if isinstance(out_shape, int):
+        out_shape = (out_shape, out_shape)
+    left = [math.ceil((i - o) / 2) for i, o in zip(img.shape, out_shape)]
+    return img[left[0]:left[0] + out_shape[0], left[1]:left[1] + out_shape[1]]
+
+
+def _prep(ary, cdtype):
+    ary = _ops.asdevice(ary)
+    if ary.dtype != cdtype:
+        ary = ary.to(cdtype)
+    return ary
+
+
+class MDFT:
+    """Matrix DFT: out = norm * Ey @ ary @ Ex.T with Ex = exp(sign*2*pi*i*outer(fx, x))
+    (prysm/fttools.py:155-232).  complex64 runs on the tcgen05 tensor cores when the shape
+    allows, otherwise (and always for complex128) on the fp32 / fp64 CUDA-core GEMM."""
+
+    def __init__(self, x, y, fx, fy, sign=-1, norm=1.0):
+        x, y, fx, fy = _host(x), _host(y), _host(fx), _host(fy)
+        cd = config.complex_dtype
+        dev = _ops.device()
+        self.Ex = _ops.mdft_basis(fx, x, sign, cd, dev)  # (len(fx), len(x))
+        self.Ey = _ops.mdft_basis(fy, y, sign, cd, dev)  # (len(fy), len(y))
+        self.norm = norm
+        Nx, Ny, Mx, My = len(x), len(y), len(fx), len(fy)
+        self._forward_left_first = My * Nx * (Ny + Mx) <= Ny * Mx * (Nx + My)
+        self._adjoint_left_first = Ny * Mx * (My + Nx) <= My * Nx * (Mx + Ny)
+
+    def __call__(self, ary):
+        return _ops.mdft_apply(self.Ey, self.Ex, _prep(ary, self.Ey.dtype), self.norm, False,
+                               self._forward_left_first)
+
+    def adjoint(self, grad):
+        return _ops.mdft_apply(self.Ey, self.Ex, _prep(grad, self.Ey.dtype), self.norm, True,
+                               self._adjoint_left_first)
+
+    def nbytes(self):
+        return self.Ex.numel() * self.Ex.element_size() + self.Ey.numel() * self.Ey.element_size()
+
+
+def _expi(turns):
+    """exp(2*pi*i*turns) for a host fp64 vector with the argument reduced first."""
+    fr = turns - np.rint(turns)
+    return np.exp(2j * np.pi * fr)
+
+
+class _CztAxis:
+    """Per-axis Bluestein pieces (prysm/fttools.py:372-389), built in fp64 on the host."""
+
+    def __init__(self, N, M, shift, alpha, sign, xc, f):
+        K = next_fast_len(N + M - 1)
+        n = np.arange(-(N // 2), -(N // 2) + N, dtype=np.float64)
+        m = np.arange(-(M // 2), -(M // 2) + M, dtype=np.float64)
+        q = m + shift
+        half = 0.5 * sign * alpha                       # exp(sign*i*pi*alpha*t^2) = expi(half*t^2)
+        a = _expi(half * q * q)
+        b = _expi(half * n * n)
+        d = np.arange(m[0] - n[-1], m[-1] - n[0] + 1, dtype=np.float64)
+        h = np.zeros(K, dtype=np.complex128)
+        h[:len(d)] = _expi(-half * (d + shift) * (d + shift))
+        H = np.fft.fft(h)
+        phase = _expi(sign * xc * f)                    # exp(sign*2*pi*i*x[N//2]*f)
+        k = np.arange(K, dtype=np.float64)
+        self.N, self.M, self.K = N, M, K
+        self.b = b                                      # applied before the forward FFT
+        self.H = H                                      # kernel spectrum
+        self.post = a * phase                           # applied to the M kept samples
+        # adjoint: embedding at offset N-1 is a linear phase on the spectrum
+        self.Hadj = np.conj(H) * _expi(-(N - 1) * k / K)
+
+
+class CZT:
+    """Chirp-z transform with the MDFT interface (prysm/fttools.py:235-369).  Each axis is two
+    fused passes: (chirp * data -> FFT_K -> * H) and (IFFT_K -> slice -> * chirp * phase)."""
+
+    def __init__(self, x, y, fx, fy, sign=-1, norm=1.0):
+        if sign not in (-1, 1):
+            raise ValueError(f'sign must be -1 or +1, got {sign}')
+        x, y, fx, fy = _host(x), _host(y), _host(fx), _host(fy)
+        self.sign, self.norm = sign, norm
+        Nx, Mx, Ny, My = len(x), len(fx), len(y), len(fy)
+        dx, dfx = float(x[1] - x[0]), float(fx[1] - fx[0])
+        dy, dfy = float(y[1] - y[0]), float(fy[1] - fy[0])
+        ax = _CztAxis(Nx, Mx, float(fx[Mx // 2]) / dfx, dx * dfx, sign, float(x[Nx // 2]), fx)
+        ay = _CztAxis(Ny, My, float(fy[My // 2]) / dfy, dy * dfy, sign, float(y[Ny // 2]), fy)
+        cd = config.complex_dtype
+        up = lambda v: _ops.asdevice(v.astype(config.precision_complex), cd)  # noqa: E731
+        self._bx, self._Hx, self._postx, self._Hadjx = up(ax.b), up(ax.H), up(ax.post), up(ax.Hadj)
+        self._by, self._Hy, self._posty, self._Hadjy = up(ay.b), up(ay.H), up(ay.post), up(ay.Hadj)
+        self._Nx, self._Ny, self._Mx, self._My, self._Kx, self._Ky = Nx, Ny, Mx, My, ax.K, ay.K
+        x_first_cost = Ny * ax.K * math.log2(ax.K) + Mx * ay.K * math.log2(ay.K)
+        y_first_cost = Nx * ay.K * math.log2(ay.K) + My * ax.K * math.log2(ax.K)
+        self._x_first = x_first_cost <= y_first_cost
+
+    def __call__(self, ary):
+        o = _prep(ary, self._bx.dtype)
+        if tuple(o.shape) != (self._Ny, self._Nx):
+            raise ValueError(f'array of shape {tuple(o.shape)} does not match the executor')
+        Kx, Ky = self._Kx, self._Ky
+        if self._x_first:
+            o = _ops.axis_dft(o, Kx, 1, -1, pre_e=self._bx, pre_b=self._by, post_e=self._Hx)
+            o = _ops.axis_dft(o, Kx, 1, +1, scale=1.0 / Kx, out_off=self._Nx - 1, n_out=self._Mx, post_e=self._postx)
+            o = _ops.axis_dft(o, Ky, 0, -1, post_e=self._Hy)
+            o = _ops.axis_dft(o, Ky, 0, +1, scale=self.norm / Ky, out_off=self._Ny - 1, n_out=self._My, post_e=self._posty)
+        else:
+            o = _ops.axis_dft(o, Ky, 0, -1, pre_e=self._by, pre_b=self._bx, post_e=self._Hy)
+            o = _ops.axis_dft(o, Ky, 0, +1, scale=1.0 / Ky, out_off=self._Ny - 1, n_out=self._My, post_e=self._posty)
+            o = _ops.axis_dft(o, Kx, 1, -1, post_e=self._Hx)
+            o = _ops.axis_dft(o, Kx, 1, +1, scale=self.norm / Kx, out_off=self._Nx - 1, n_out=self._Mx, post_e=self._postx)
+        return o
+
+    def adjoint(self, grad):
+        o = _prep(grad, self._bx.dtype)
+        if tuple(o.shape) != (self._My, self._Mx):
+            raise ValueError(f'array of shape {tuple(o.shape)} does not match the executor')
+        Kx, Ky = self._Kx, self._Ky
+        if self._x_first:  # undo y then x
+            o = _ops.axis_dft(o, Ky, 0, -1, pre_e=self._posty, pre_e_conj=True, pre_b=self._postx, pre_b_conj=True,
+                              post_e=self._Hadjy)
+            o = _ops.axis_dft(o, Ky, 0, +1, scale=1.0 / Ky, n_out=self._Ny)
+            o = _ops.axis_dft(o, Kx, 1, -1, post_e=self._Hadjx)
+            o = _ops.axis_dft(o, Kx, 1, +1, scale=self.norm / Kx, n_out=self._Nx, post_e=self._bx, post_e_conj=True,
+                              post_b=self._by, post_b_conj=True)
+        else:
+            o = _ops.axis_dft(o, Kx, 1, -1, pre_e=self._postx, pre_e_conj=True, pre_b=self._posty, pre_b_conj=True,
+                              post_e=self._Hadjx)
+            o = _ops.axis_dft(o, Kx, 1, +1, scale=1.0 / Kx, n_out=self._Nx)
+            o = _ops.axis_dft(o, Ky, 0, -1, post_e=self._Hadjy)
+            o = _ops.axis_dft(o, Ky, 0, +1, scale=self.norm / Ky, n_out=self._Ny, post_e=self._by, post_e_conj=True,
+                              post_b=self._bx, post_b_conj=True)
+        return o
+
+    def nbytes(self):
+        return sum(v.numel() * v.element_size() for v in (self._bx, self._Hx, self._postx, self._Hadjx,
+                                                          self._by, self._Hy, self._posty, self._Hadjy))
+
+
+def _uniform_spacing(values, name):
+    """prysm/fttools.py:484-497 (same messages)."""
+    if len(values) < 2:
+        raise ValueError(f'{name} must contain at least two samples')
+    spacing = float(values[1] - values[0])
+    if spacing == 0:
+        raise ValueError(f'{name} must have nonzero spacing')
+    tolerance = 32 * np.finfo(config.precision).eps
+    scale = max(1.0, abs(float(values[0])), abs(float(values[-1])), abs(spacing))
+    if not bool(np.allclose(np.diff(values), spacing, rtol=tolerance, atol=tolerance * scale)):
+        raise ValueError(f'{name} must be uniformly spaced')
+    return spacing
+
+
+def _fft_compatible_length(alpha, N, M, name):
+    """prysm/fttools.py:500-514 (same messages)."""
+    inv_alpha = 1 / abs(alpha)
+    K = round(inv_alpha)
+    tolerance = 32 * np.finfo(config.precision).eps
+    if not math.isclose(inv_alpha, K, rel_tol=tolerance, abs_tol=tolerance):
+        raise ValueError(f'{name} spacings are not FFT-compatible: '
+                         'abs(input spacing * output spacing) must be 1/integer')
+    if K < max(N, M):
+        raise ValueError(f'{name} requires FFT length {K}, smaller than input/output length {max(N, M)}')
+    return K
+
+
+class FFTDFT:
+    """DFT as one FFT per axis when dx*dfx = +-1/K (prysm/fttools.py:392-481): phase ramp ->
+    FFT_K -> crop, with the ramps fused into the two passes."""
+
+    def __init__(self, x, y, fx, fy, sign=-1, norm=1.0):
+        if sign not in (-1, 1):
+            raise ValueError(f'sign must be -1 or +1, got {sign}')
+        x, y, fx, fy = _host(x), _host(y), _host(fx), _host(fy)
+        Nx, Ny, Mx, My = len(x), len(y), len(fx), len(fy)
+        dx, dy = _uniform_spacing(x, 'x'), _uniform_spacing(y, 'y')
+        dfx, dfy = _uniform_spacing(fx, 'fx'), _uniform_spacing(fy, 'fy')
+        Kx = _fft_compatible_length(dx * dfx, Nx, Mx, 'x/fx')
+        Ky = _fft_compatible_length(dy * dfy, Ny, My, 'y/fy')
+        cd = config.complex_dtype
+        up = lambda v: _ops.asdevice(v.astype(config.precision_complex), cd)  # noqa: E731
+        self._pre_x = up(_expi(sign * np.arange(Nx) * dx * float(fx[0])))
+        self._pre_y = up(_expi(sign * np.arange(Ny) * dy * float(fy[0])))
+        self._post_x = up(_expi(sign * float(x[0]) * fx))
+        self._post_y = up(_expi(sign * float(y[0]) * fy))
+        self._Nx, self._Ny, self._Mx, self._My, self._Kx, self._Ky = Nx, Ny, Mx, My, Kx, Ky
+        self._x_direction = sign if dx * dfx > 0 else -sign
+        self._y_direction = sign if dy * dfy > 0 else -sign
+        self.norm = norm
+        x_first_cost = Ny * Kx * math.log2(Kx) + Mx * Ky * math.log2(Ky)
+        y_first_cost = Nx * Ky * math.log2(Ky) + My * Kx * math.log2(Kx)
+        self._x_first = x_first_cost <= y_first_cost
+
+    def __call__(self, ary):
+        o = _prep(ary, self._pre_x.dtype)
+        if tuple(o.shape) != (self._Ny, self._Nx):
+            raise ValueError(f'array of shape {tuple(o.shape)} does not match the executor')
+        if self._x_first:
+            o = _ops.axis_dft(o, self._Kx, 1, self._x_direction, pre_e=self._pre_x, pre_b=self._pre_y,
+                              n_out=self._Mx, post_e=self._post_x)
+            o = _ops.axis_dft(o, self._Ky, 0, self._y_direction, n_out=self._My, post_e=self._post_y, scale=self.norm)
+        else:
+            o = _ops.axis_dft(o, self._Ky, 0, self._y_direction, pre_e=self._pre_y, pre_b=self._pre_x,
+                              n_out=self._My, post_e=self._post_y)
+            o = _ops.axis_dft(o, self._Kx, 1, self._x_direction, n_out=self._Mx, post_e=self._post_x, scale=self.norm)
+        return o
+
+    def adjoint(self, grad):
+        o = _prep(grad, self._pre_x.dtype)
+        if tuple(o.shape) != (self._My, self._Mx):
+            raise ValueError(f'array of shape {tuple(o.shape)} does not match the executor')
+        if self._x_first:
+            o = _ops.axis_dft(o, self._Ky, 0, -self._y_direction, pre_e=self._post_y, pre_e_conj=True,
+                              pre_b=self._post_x, pre_b_conj=True, n_out=self._Ny, post_e=self._pre_y, post_e_conj=True)
+            o = _ops.axis_dft(o, self._Kx, 1, -self._x_direction, n_out=self._Nx, post_e=self._pre_x, post_e_conj=True,
+                              scale=self.norm)
+        else:
+            o = _ops.axis_dft(o, self._Kx, 1, -self._x_direction, pre_e=self._post_x, pre_e_conj=True,
+                              pre_b=self._post_y, pre_b_conj=True, n_out=self._Nx, post_e=self._pre_x, post_e_conj=True)
+            o = _ops.axis_dft(o, self._Ky, 0, -self._y_direction, n_out=self._Ny, post_e=self._pre_y, post_e_conj=True,
+                              scale=self.norm)
+        return o
+
+    def nbytes(self):
+        return sum(v.numel() * v.element_size() for v in (self._pre_x, self._pre_y, self._post_x, self._post_y))

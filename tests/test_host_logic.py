@@ -1,0 +1,82 @@
+"""CPU: host-side logic of the mirror API that needs no kernel launch -- argument checks,
+error types / messages, shape and sample-spacing bookkeeping, executor planning."""
+import math
+
+import numpy as np
+import pytest
+
+from prysm_b200 import propagation, fttools
+from prysm_b200.conf import config, Config
+
+
+def test_config_precision_like_reference():
+    c = Config()
+    assert c.precision is np.float64 and c.precision_complex is np.complex128
+    c.precision = 32
+    assert c.precision is np.float32 and c.precision_complex is np.complex64
+    c.precision = 'float64'
+    assert c.precision is np.float64
+    with pytest.raises(ValueError):
+        c.precision = 'int32'
+    with pytest.raises(ValueError):
+        c.precision = 'not a dtype'
+
+
+def test_sample_spacing_helpers():
+    assert propagation.pupil_sample_to_psf_sample(10 / 2048, 4096, 0.6328, 100.0) == pytest.approx(3.164)
+    assert propagation.psf_sample_to_pupil_sample(3.164, 4096, 0.6328, 100.0) == pytest.approx(10 / 2048)
+    assert propagation.Q_for_sampling(10.0, 100.0, 0.5, 2.5) == pytest.approx(2.0)
+    assert propagation.phase_prefix(0.5) == pytest.approx(1j * 2 * np.pi / 0.5 / 1e3)
+    fdx, n = propagation.unit_cell_focal_grid(0.1, 10.0, 0.6328, 100.0, Q=2)
+    assert n == 200 and fdx == pytest.approx(0.6328 * 100 / 0.1 / 200)
+
+
+def test_padded_shapes_follow_pad2d_rule():
+    assert propagation._padded_shape((9, 12), 1.5) == (14, 18)
+    assert propagation._padded_shape((7, 9), 2) == (14, 18)
+    assert propagation._padded_shape((8, 8), 1) == (8, 8)
+    assert propagation._shape_before_pad((14, 18), 1.5) == (9, 12)
+
+
+def test_coordinates_for_focus_matches_oracle():
+    import prysm_oracle as O
+    config.precision = 64
+    got = propagation.coordinates_for_focus(0.1, (9, 12), 1.7, (8, 11), 0.6328, 100.0, (3.0, -2.0))
+    want = O.coordinates_for_focus(0.1, (9, 12), 1.7, (8, 11), 0.6328, 100.0, (3.0, -2.0))
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+def test_next_fast_len_is_power_of_two():
+    for n, want in ((1, 1), (2, 2), (3, 4), (4095, 4096), (4607, 8192), (4096, 4096)):
+        assert fttools.next_fast_len(n) == want
+
+
+def test_fftdft_validation_messages():
+    config.precision = 64
+    with pytest.raises(ValueError, match='uniformly spaced'):
+        fttools._uniform_spacing(np.array([0.0, 1.0, 2.5]), 'x')
+    with pytest.raises(ValueError, match='at least two samples'):
+        fttools._uniform_spacing(np.array([0.0]), 'x')
+    with pytest.raises(ValueError, match='not FFT-compatible'):
+        fttools._fft_compatible_length(1 / 10.3, 8, 8, 'x/fx')
+    with pytest.raises(ValueError, match='smaller than input/output'):
+        fttools._fft_compatible_length(1 / 8, 16, 8, 'x/fx')
+    assert fttools._fft_compatible_length(-1 / 32, 16, 32, 'x/fx') == 32
+
+
+def test_prepare_executor_bad_kind():
+    with pytest.raises(ValueError, match="kind must be 'mdft', 'czt', or 'fftdft'"):
+        propagation.prepare_executor(0.1, 8, 1.0, 8, 0.5, 100.0, kind='nope')
+
+
+def test_czt_axis_plan_matches_oracle_basis():
+    """The fp64 host plan (chirps, kernel spectrum) equals the oracle's _czt_axis_basis up to the
+    different internal K (any K >= N+M-1 gives the same transform)."""
+    import prysm_oracle as O
+    N, M, shift, alpha = 12, 11, 1.25, 0.013
+    ax = fttools._CztAxis(N, M, shift, alpha, -1, 0.0, np.zeros(M))
+    H, b, a = O._czt_axis_basis(N, M, ax.K, shift, alpha, np.float64, np.complex128, -1)
+    assert np.allclose(ax.b, b, atol=1e-14) and np.allclose(ax.post, a, atol=1e-14)
+    assert np.allclose(ax.H, H, atol=1e-12)
+    assert ax.K == 32 and math.log2(ax.K).is_integer()
