@@ -166,8 +166,10 @@ def talbot_distance(a, lambda_):
 # array API: fixed-sampling executors (prysm/propagation/dft.py)
 # ------------------------------------------------------------------------------------------
 
-def coordinates_for_focus(pupil_dx, pupil_samples, focal_dx, focal_samples, wavelength, efl, focal_shift=(0, 0)):
-    """x, y [mm] and fx, fy [1/mm] as host arrays at config.precision (prysm/propagation/dft.py:12-66)."""
+def coordinates_for_focus(pupil_dx, pupil_samples, focal_dx, focal_samples, wavelength, efl, focal_shift=(0, 0),
+                          dtype=None):
+    """x, y [mm] and fx, fy [1/mm] as host arrays at config.precision (prysm/propagation/dft.py:12-66).
+    `dtype` overrides the precision of the returned vectors."""
     if not isinstance(pupil_samples, Iterable):
         pupil_samples = (pupil_samples, pupil_samples)
     if not isinstance(focal_samples, Iterable):
@@ -175,7 +177,7 @@ def coordinates_for_focus(pupil_dx, pupil_samples, focal_dx, focal_samples, wave
     pny, pnx = pupil_samples
     fny, fnx = focal_samples
     fsx, fsy = focal_shift
-    dt = config.precision
+    dt = config.precision if dtype is None else dtype
 
     def rng(n):
         return np.arange(-(n // 2), -(n // 2) + n, dtype=dt)
@@ -192,8 +194,10 @@ def prepare_executor(pupil_dx, pupil_samples, focal_dx, focal_samples, wavelengt
                      kind='mdft'):
     """Reusable pupil <-> focal operator with norm = pupil_dx*focal_dx/(wvl*efl) baked in
     (prysm/propagation/dft.py:69-117)."""
+    # coordinates stay in fp64 whatever config.precision is: differencing float32 grids (as the
+    # reference does at precision=32) costs ~1e-6 in the chirp rate before any transform runs
     x, y, fx, fy = coordinates_for_focus(pupil_dx, pupil_samples, focal_dx, focal_samples, wavelength, efl,
-                                         focal_shift)
+                                         focal_shift, dtype=np.float64)
     norm = (pupil_dx * focal_dx) / (wavelength * efl)
     if kind == 'mdft':
         op = MDFT(x, y, fx, fy, sign=-1, norm=norm)
