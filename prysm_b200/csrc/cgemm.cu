@@ -29,6 +29,9 @@ __global__ void __launch_bounds__(256) cgemm_kernel(int M, int N, int K, R alpha
     const int tid = threadIdx.x;
     const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
     const int tx = tid & 15, ty = tid >> 4;
+    // two-level accumulation: 64-term partial sums are folded into the running total, which keeps the
+    // rounding error of a K = 4096 contraction near sqrt(64) + sqrt(K/64) ulp instead of sqrt(K)
+    R tr[4][4] = {}, ti[4][4] = {};
     R cr[4][4] = {}, ci[4][4] = {};
     for (int k0 = 0; k0 < K; k0 += BK) {
         for (int e = tid; e < BM * BK; e += 256) {
@@ -65,13 +68,22 @@ __global__ void __launch_bounds__(256) cgemm_kernel(int M, int N, int K, R alpha
                 }
         }
         __syncthreads();
+        if (((k0 / BK) & 3) == 3) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    tr[u][v] += cr[u][v]; ti[u][v] += ci[u][v];
+                    cr[u][v] = R(0); ci[u][v] = R(0);
+                }
+        }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             const int i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
-            if (i < M && j < N) C[(long long)i * ldc + j] = mk<R>(alpha * cr[u][v], alpha * ci[u][v]);
+            if (i < M && j < N) C[(long long)i * ldc + j] = mk<R>(alpha * (tr[u][v] + cr[u][v]), alpha * (ti[u][v] + ci[u][v]));
         }
 }
 

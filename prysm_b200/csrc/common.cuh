@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <complex>
 #include <cstdio>
 #include <map>
 #include <string>
@@ -91,6 +92,8 @@ inline int fail(Handle* h, int code, const std::string& msg) {
 int ensure_scratch(Handle* h, int slot, size_t bytes, void** out);
 // device table of w_n^k = exp(-2*pi*i*k/n), k in [0,n)
 int get_twiddles(Handle* h, int n, int dtype, const void** out);
+// upload a host fp64 complex table in the precision of key.dtype and cache it in the handle
+int upload_table(Handle* h, const TwKey& key, const std::vector<std::complex<double>>& t, const void** out);
 
 inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 inline int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }

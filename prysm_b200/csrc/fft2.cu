@@ -34,7 +34,7 @@ static void host_fft_pow2(std::vector<std::complex<double>>& a, int sign) {
     }
 }
 
-static int upload_table(Handle* h, const TwKey& key, const std::vector<std::complex<double>>& t, const void** out) {
+int upload_table(Handle* h, const TwKey& key, const std::vector<std::complex<double>>& t, const void** out) {
     const size_t n = t.size();
     void* d = nullptr;
     PB_CUDA(h, cudaMalloc(&d, n * csize(key.dtype)));

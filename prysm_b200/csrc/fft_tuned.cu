@@ -4,24 +4,31 @@
 // Algebra.  K = 2N.  focus = fftshift(FFT2_K(ifftshift(pad(x)))).  Along one axis, with q = x
 // zero-extended to K:   U[k] = (-dir*i)^k * Q[k]   (the centred pad + ifftshift is a circular
 // shift by K/4), and the zero half makes the first radix-2 level trivial:
-//      Q[2j]   = FFT_N(x)[j]                    ("even" half)
-//      Q[2j+1] = FFT_N(x * w_K^n)[j]            ("odd" half)
+//      Q[2j]   = FFT_N(x)[j]                    ("even" half, lane A)
+//      Q[2j+1] = FFT_N(x * w_K^n)[j]            ("odd" half,  lane B)
 // so every length-K transform of the padded data is two length-N transforms of the un-padded
 // data, the shifts are sign patterns / index rotations at the store, and no zero is ever read,
 // written or multiplied.
 //
-// Data flow (columns first so that the big K x K output is written by the row kernel in full
-// 32 KB rows with 128-bit stores):
-//   phase p in {even, odd} output rows:
-//     focus_col_kernel : FFT_N down T adjacent columns of the pupil (x w_K^n for the odd phase)
-//                        -> N x N intermediate (rows j  <->  output row 2j+p, rotated by K/2)
-//     focus_row_kernel : per intermediate row, the two FFT_N (even / odd output columns) in one CTA,
-//                        outputs interleaved so each thread stores 16 contiguous bytes
-//   HBM traffic: pupil 8N^2 (+ a second read that mostly hits L2), output 8K^2; the N x N x 8 B
-//   intermediate of each phase (32 MiB at N = 2048) is produced and consumed inside the 126 MB L2.
+// Packed arithmetic.  sm_100 issues two fp32 operations per instruction on 64-bit register pairs
+// (FADD2 / FMUL2 / FFMA2).  Each thread therefore carries BOTH half-transforms of its line in
+// structure-of-arrays form -- re = (re_A, re_B), im = (im_A, im_B) -- and every butterfly, twiddle
+// multiply and store acts on the pair: the instruction count of the FFT is halved and the kernels
+// move from issue-bound to FP32-pipe-bound.  The two lanes differ only in their inputs
+// (lane B = x * w_32^n, immediates) and in the stage-1 twiddle (w_K^t folded into lane B's table entry).
 //
-// FFT_N engine: N/16 threads per transform, 16 points per thread in registers, radix 16 x 16 x N/256,
-// two shared-memory exchanges (1-in-16 padded, conflict free), twiddles from an L1-resident table.
+// Data flow (columns first so that the K x K output is written by the row kernel in full rows with
+// 128-bit stores):
+//   focus_col_kernel : FFT_N down T adjacent columns of the pupil, both halves ->
+//                      intermediate [2][N][N] (plane p, row j  <->  output row 2j+p, rotated by K/2)
+//   focus_row_kernel : persistent; per intermediate row both half-transforms; thread owns outputs
+//                      (2j, 2j+1) and stores them as one float4.  Rows arrive by bulk async copy
+//                      (cp.async.bulk + mbarrier), one row ahead.
+//   HBM traffic: pupil 8N^2 once, output 8K^2 once; the 16N^2-byte intermediate (64 MiB at N = 2048)
+//   is written and re-read through the 126 MB L2.
+//
+// FFT_N engine: N/16 threads per line, 16 points x 2 lanes per thread in registers, radix
+// 16 x 16 x N/256, two shared-memory exchanges of float4 (1-in-16 padded, conflict free).
 #include <cstdlib>
 #include "fft_tuned.cuh"
 
@@ -32,34 +39,38 @@ namespace {
 #define PB_C1_8 0.92387953251128675613f   // cos(pi/8)
 #define PB_S1_8 0.38268343236508977173f   // sin(pi/8)
 
-__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 fcmul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
+// two complex numbers (lane A, lane B), structure of arrays
+struct P2 { float2 re, im; };
+
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ P2 operator+(P2 a, P2 b) { return {__fadd2_rn(a.re, b.re), __fadd2_rn(a.im, b.im)}; }
+__device__ __forceinline__ P2 operator-(P2 a, P2 b) { return {__fadd2_rn(a.re, neg2(b.re)), __fadd2_rn(a.im, neg2(b.im))}; }
 // multiply by w4 = exp(-+ i pi/2):  -i forward, +i inverse
-template <bool INV> __device__ __forceinline__ float2 mul_w4(float2 a) {
-    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+template <bool INV> __device__ __forceinline__ P2 mul_w4(P2 a) { return INV ? P2{neg2(a.im), a.re} : P2{a.im, neg2(a.re)}; }
+// multiply both lanes by w = (c, -+ s)
+template <bool INV> __device__ __forceinline__ P2 mul_cs(P2 a, float c, float s) {
+    const float2 C = make_float2(c, c), S = make_float2(s, s);
+    if (INV) return {__ffma2_rn(a.re, C, neg2(__fmul2_rn(a.im, S))), __ffma2_rn(a.im, C, __fmul2_rn(a.re, S))};
+    return {__ffma2_rn(a.re, C, __fmul2_rn(a.im, S)), __ffma2_rn(a.im, C, neg2(__fmul2_rn(a.re, S)))};
 }
-// multiply by w = (c, -+ s)
-template <bool INV> __device__ __forceinline__ float2 mul_cs(float2 a, float c, float s) {
-    return INV ? make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.y, c, a.x * s))
-               : make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s));
+// per-lane twiddle: w = (wre, wim) pairs as stored in the tables (forward sign); INV conjugates
+template <bool INV> __device__ __forceinline__ P2 mul_tw(P2 a, float4 w) {
+    const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
+    if (INV) return {__ffma2_rn(a.re, wr, __fmul2_rn(a.im, wi)), __ffma2_rn(a.im, wr, neg2(__fmul2_rn(a.re, wi)))};
+    return {__ffma2_rn(a.re, wr, neg2(__fmul2_rn(a.im, wi))), __ffma2_rn(a.im, wr, __fmul2_rn(a.re, wi))};
 }
 
-template <bool INV> __device__ __forceinline__ void dft2(float2& a, float2& b) {
-    float2 s = a + b, d = a - b;
+template <bool INV> __device__ __forceinline__ void dft2(P2& a, P2& b) {
+    P2 s = a + b, d = a - b;
     a = s; b = d;
 }
-
-template <bool INV> __device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
-    float2 s02 = x0 + x2, d02 = x0 - x2, s13 = x1 + x3, d13 = mul_w4<INV>(x1 - x3);
+template <bool INV> __device__ __forceinline__ void dft4(P2& x0, P2& x1, P2& x2, P2& x3) {
+    P2 s02 = x0 + x2, d02 = x0 - x2, s13 = x1 + x3, d13 = mul_w4<INV>(x1 - x3);
     x0 = s02 + s13; x2 = s02 - s13; x1 = d02 + d13; x3 = d02 - d13;
 }
-
-template <bool INV> __device__ __forceinline__ void dft8(float2* v) {
-    float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
-    float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+template <bool INV> __device__ __forceinline__ void dft8(P2* v) {
+    P2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    P2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
     dft4<INV>(e0, e1, e2, e3);
     dft4<INV>(o0, o1, o2, o3);
     o1 = mul_cs<INV>(o1, PB_SQRT1_2, PB_SQRT1_2);
@@ -70,9 +81,8 @@ template <bool INV> __device__ __forceinline__ void dft8(float2* v) {
     v[2] = e2 + o2; v[6] = e2 - o2;
     v[3] = e3 + o3; v[7] = e3 - o3;
 }
-
-template <bool INV> __device__ __forceinline__ void dft16(float2* v) {
-    float2 e[8], o[8];
+template <bool INV> __device__ __forceinline__ void dft16(P2* v) {
+    P2 e[8], o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
     dft8<INV>(e);
@@ -87,84 +97,193 @@ template <bool INV> __device__ __forceinline__ void dft16(float2* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i] = e[i] + o[i]; v[i + 8] = e[i] - o[i]; }
 }
-
-template <int R, bool INV> __device__ __forceinline__ void dftR(float2* v) {
+template <int R, bool INV> __device__ __forceinline__ void dftR(P2* v) {
     if (R == 2) dft2<INV>(v[0], v[1]);
     else if (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
     else if (R == 8) dft8<INV>(v);
     else dft16<INV>(v);
 }
 
+__device__ __forceinline__ float4 pack(P2 a) { return make_float4(a.re.x, a.re.y, a.im.x, a.im.y); }
+__device__ __forceinline__ P2 unpack(float4 a) { return {make_float2(a.x, a.y), make_float2(a.z, a.w)}; }
+
+// lane A = x, lane B = x * w_32^n (the n-dependent part of the odd half's input ramp), compile-time n
+template <bool INV, int n> __device__ __forceinline__ P2 make_lanes(float2 x) {
+    // w_32^n = (cos(2 pi n/32), -sin(2 pi n/32))
+    constexpr float C[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                             0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                             0.19509032201612826785f, 0.0f, -0.19509032201612826785f, -0.38268343236508977173f,
+                             -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                             -0.92387953251128675613f, -0.98078528040323044913f};
+    constexpr float Sn[16] = {0.0f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                              0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                              0.98078528040323044913f, 1.0f, 0.98078528040323044913f, 0.92387953251128675613f,
+                              0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                              0.38268343236508977173f, 0.19509032201612826785f};
+    const float c = C[n], s = INV ? -Sn[n] : Sn[n];          // x * (c - i s)
+    float2 b;
+    if (n == 0) b = x;
+    else if (n == 8) b = make_float2(x.y * s, -x.x * s);     // c = 0
+    else b = make_float2(fmaf(x.x, c, x.y * s), fmaf(x.y, c, -x.x * s));
+    return {make_float2(x.x, b.x), make_float2(x.y, b.y)};
+}
+
 __device__ __forceinline__ int pad16(int a) { return a + (a >> 4); }
 
-struct SyncCta { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
-struct SyncNamed {
-    int id, count;
-    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-};
+// ---- cache-policy loads / stores --------------------------------------------------------------------
+// The only data with reuse inside an SM is the twiddle plan: it is pinned in L1 (evict_last) and every
+// streaming access bypasses L1 allocation so that it cannot displace the plan.
+__device__ __forceinline__ float4 ld_plan(const float4* p) {
+    float4 r;
+    asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+    float2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream(float2* p, float2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
 
-// First two radix-16 stages of FFT_L (L >= 512).  In: v[n] = x[n*L/16 + t].  Out: the stage-2 results in S
-// (1-in-16 padded, position-major) ready for the final radix-(L/256) stage:  item i in [0, 256) reads
-// S[pad16(n*256 + i)], n < L/256, and after dft produces X[i + 256*k].   tw: w_TL^j table, TLS = TL / L.
-template <int L, bool INV, int TLS, class Sync>
-__device__ __forceinline__ void fft_two_stages(float2 (&v)[16], const int t, float2* __restrict__ S,
-                                               const float2* __restrict__ tw, Sync sync) {
-    constexpr int NT = L / 16;
-    dft16<INV>(v);
-#pragma unroll
-    for (int k = 1; k < 16; ++k) {
-        float2 w = __ldg(tw + t * k * TLS);
-        if (INV) w.y = -w.y;
-        v[k] = fcmul(v[k], w);
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) S[t * 17 + k] = v[k];
-    sync();
-#pragma unroll
-    for (int n = 0; n < 16; ++n) v[n] = S[pad16(n * NT + t)];
-    sync();
-    dft16<INV>(v);
-    const int m = t >> 4, a = t & 15;
-#pragma unroll
-    for (int k = 1; k < 16; ++k) {
-        float2 w = __ldg(tw + m * k * 16 * TLS);
-        if (INV) w.y = -w.y;
-        v[k] = fcmul(v[k], w);
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) S[m * 272 + a + 17 * k] = v[k];
-    sync();
+// ---- async-copy plumbing (cp.async.bulk = the 1-D TMA path; completion on an mbarrier) -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 template <int L> struct Geo {
-    static constexpr int NT = L / 16;          // threads per transform
+    static constexpr int NT = L / 16;          // threads per line
     static constexpr int R3 = L / 256;         // last radix
-    static constexpr int SBUF = L + L / 16;    // padded exchange buffer, complex elements
+    static constexpr int GI = 16 / R3;         // last-stage items per thread
+    static constexpr int SBUF = L + L / 16;    // padded exchange buffer, float4 elements
+    // plan table layout (float4 elements):
+    //   TW1[k][t], k < 16 : (w_L^(tk).re, (w_L^(tk) w_2L^t).re, w_L^(tk).im, (w_L^(tk) w_2L^t).im)
+    //   TW2[k-1][m], 1 <= k < 16, m < NT/16 : (wr, wr, wi, wi), w = w_L^(16 m k)
+    static constexpr int TW1 = 0, TW2 = 16 * NT, PLAN = 16 * NT + 15 * (NT / 16);
 };
+
+// First two radix-16 stages on both lanes.  In: v[n] = lanes of x[n*NT + t].  Out: stage-2 results in S
+// (float4, 1-in-16 padded, position-major): final-stage item i in [0, 256) reads S[pad16(n*256 + i)],
+// n < L/256, and after the radix-(L/256) dft holds X[i + 256*k].
+template <int L, bool INV, bool PLAN_SMEM, class Sync1, class Sync>
+__device__ __forceinline__ void fft_two_stages(P2 (&v)[16], const int t, float4* __restrict__ S,
+                                               const float4* __restrict__ plan, Sync1 sync1, Sync sync) {
+    using G = Geo<L>;
+    constexpr int NT = G::NT;
+    dft16<INV>(v);
+    {
+        const float4* __restrict__ w1 = plan + G::TW1 + t;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = mul_tw<INV>(v[k], PLAN_SMEM ? w1[k * NT] : ld_plan(w1 + k * NT));
+    }
+    {
+        float4* __restrict__ d = S + t * 17;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = pack(v[k]);
+    }
+    sync1();
+    {
+        const float4* __restrict__ s = S + pad16(t);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) v[n] = unpack(s[n * (NT + NT / 16)]);
+    }
+    sync();
+    dft16<INV>(v);
+    const int m = t >> 4, a = t & 15;
+    {
+        const float4* __restrict__ w2 = plan + G::TW2 + m;
+#pragma unroll
+        for (int k = 1; k < 16; ++k) v[k] = mul_tw<INV>(v[k], PLAN_SMEM ? w2[(k - 1) * (NT / 16)] : ld_plan(w2 + (k - 1) * (NT / 16)));
+    }
+    {
+        float4* __restrict__ d = S + m * 272 + a;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[17 * k] = pack(v[k]);
+    }
+    sync();
+}
+
+// final radix-(L/256) stage inputs: afterwards v[g*R3 + n] holds the n-th input of item t + g*NT
+template <int L, bool INV>
+__device__ __forceinline__ void fft_last_stage_load(P2 (&v)[16], const int t, const float4* __restrict__ S) {
+    using G = Geo<L>;
+    const float4* __restrict__ s = S + pad16(t);
+#pragma unroll
+    for (int g = 0; g < G::GI; ++g)
+#pragma unroll
+        for (int n = 0; n < G::R3; ++n) v[g * G::R3 + n] = unpack(s[n * 272 + g * (G::NT + G::NT / 16)]);
+}
+
+#define PB_MAKE_LANES_16(v, INV, X)                                                                         \
+    v[0] = make_lanes<INV, 0>(X(0));   v[1] = make_lanes<INV, 1>(X(1));   v[2] = make_lanes<INV, 2>(X(2));     \
+    v[3] = make_lanes<INV, 3>(X(3));   v[4] = make_lanes<INV, 4>(X(4));   v[5] = make_lanes<INV, 5>(X(5));     \
+    v[6] = make_lanes<INV, 6>(X(6));   v[7] = make_lanes<INV, 7>(X(7));   v[8] = make_lanes<INV, 8>(X(8));     \
+    v[9] = make_lanes<INV, 9>(X(9));   v[10] = make_lanes<INV, 10>(X(10)); v[11] = make_lanes<INV, 11>(X(11)); \
+    v[12] = make_lanes<INV, 12>(X(12)); v[13] = make_lanes<INV, 13>(X(13)); v[14] = make_lanes<INV, 14>(X(14)); \
+    v[15] = make_lanes<INV, 15>(X(15));
+
+struct SyncCta { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
 struct FocusParams {
     // column kernel input
     const void* in; int in_kind; const void* amp; int amp_kind; double kturns; long long in_ld;
-    float2* tmp;            // [phases][N][N] intermediate
-    const float2* tw;       // w_K^j, K = 2N entries
+    float2* tmp;            // [2][N][N] intermediate (plane 0: even output rows, plane 1: odd)
+    const float4* plan;     // Geo<N> plan table
     // row kernel output
     void* out; long long out_ld; int out_kind; float scale; float weight;
-    int phase0;             // first phase handled by this launch (blockIdx.y adds to it)
+    int nrows;              // row kernel: 2N
 };
 
-// ---- column pass: FFT_N down T adjacent columns --------------------------------------------------
+// ---- column pass: both half-transforms down T adjacent columns -------------------------------------
 template <int L, bool INV, int T>
 __global__ void __launch_bounds__(T * L / 16) focus_col_kernel(const FocusParams p) {
     using G = Geo<L>;
-    extern __shared__ __align__(16) float2 smem[];
+    extern __shared__ __align__(128) float4 smem4[];
+    float4* plan_s = smem4 + T * (G::SBUF + 2);                       // the twiddle plan, bulk-copied once
+    uint64_t* bar = reinterpret_cast<uint64_t*>(plan_s + G::PLAN);
     const int c = threadIdx.x % T, t = threadIdx.x / T;
     const int col = blockIdx.x * T + c;
-    const int phase = p.phase0 + blockIdx.y;
-    float2 v[16];
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, G::PLAN * sizeof(float4));
+        bulk_g2s(plan_s, p.plan, G::PLAN * sizeof(float4), bar);
+    }
+    __syncthreads();
+    P2 v[16];
+    float2 x[16];
     if (p.in_kind == PB_IN_COMPLEX) {
-        const float2* __restrict__ src = reinterpret_cast<const float2*>(p.in) + col;
+        const float2* __restrict__ src = reinterpret_cast<const float2*>(p.in) + col + (long long)t * p.in_ld;
+        const long long step = (long long)G::NT * p.in_ld;
 #pragma unroll
-        for (int n = 0; n < 16; ++n) v[n] = __ldg(src + (long long)(n * G::NT + t) * p.in_ld);
+        for (int n = 0; n < 16; ++n) x[n] = ld_stream(src + n * step);
     } else {
         const float* __restrict__ opd = reinterpret_cast<const float*>(p.in) + col;
 #pragma unroll
@@ -178,135 +297,176 @@ __global__ void __launch_bounds__(T * L / 16) focus_col_kernel(const FocusParams
                 e = expi_turns(p.kturns * (double)__ldg(opd + off), 0.0f);
                 e.x *= a; e.y *= a;
             }
-            v[n] = e;
+            x[n] = e;
         }
     }
-    if (phase) {  // odd output rows: modulate by w_K^n
+#define PB_X(n) x[n]
+    PB_MAKE_LANES_16(v, INV, PB_X)
+#undef PB_X
+    float4* S = smem4 + c * (G::SBUF + 2);  // +2: skews the T buffers across banks
+    mbar_wait(bar, 0);
+    fft_two_stages<L, INV, true>(v, t, S, plan_s, SyncCta(), SyncCta());
+    fft_last_stage_load<L, INV>(v, t, S);
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {
-            float2 w = __ldg(p.tw + n * G::NT + t);
-            if (INV) w.y = -w.y;
-            v[n] = fcmul(v[n], w);
-        }
-    }
-    float2* S = smem + c * (G::SBUF + 4);  // +4: skews the T buffers across banks
-    fft_two_stages<L, INV, 2>(v, t, S, p.tw, SyncCta());
-    constexpr int R3 = G::R3, GI = 16 / R3;
-#pragma unroll
-    for (int g = 0; g < GI; ++g)
-#pragma unroll
-        for (int n = 0; n < R3; ++n) v[g * R3 + n] = S[pad16(n * 256 + t + g * G::NT)];
-#pragma unroll
-    for (int g = 0; g < GI; ++g) dftR<R3, INV>(v + g * R3);
-    // (-dir*i)^k with k = 2j + phase; j = t + g*NT + 256*kk has the parity of t
+    for (int g = 0; g < G::GI; ++g) dftR<G::R3, INV>(v + g * G::R3);
+    // (-dir*i)^k with k = 2j + lane; j = t + g*NT + 256*kk has the parity of t
     const float sgn = (t & 1) ? -1.0f : 1.0f;
-    float2* __restrict__ dst = p.tmp + (long long)blockIdx.y * L * L + col;
+    float2* __restrict__ dA = p.tmp + col + (long long)t * L;
+    float2* __restrict__ dB = dA + (long long)L * L;
 #pragma unroll
-    for (int g = 0; g < GI; ++g)
+    for (int g = 0; g < G::GI; ++g)
 #pragma unroll
-        for (int kk = 0; kk < R3; ++kk) {
-            const int j = t + g * G::NT + 256 * kk;
-            float2 x = v[g * R3 + kk];
-            if (phase) x = INV ? make_float2(x.y, -x.x) : make_float2(-x.y, x.x);  // * (-dir*i)
-            dst[(long long)j * L] = make_float2(sgn * x.x, sgn * x.y);
+        for (int kk = 0; kk < G::R3; ++kk) {
+            const P2 y = v[g * G::R3 + kk];
+            const long long o = (long long)(g * G::NT + 256 * kk) * L;
+            st_stream(dA + o, make_float2(sgn * y.re.x, sgn * y.im.x));
+            // lane B times (-dir*i): forward (+i): (-im, re); inverse (-i): (im, -re)
+            st_stream(dB + o, INV ? make_float2(sgn * y.im.y, -sgn * y.re.y) : make_float2(-sgn * y.im.y, sgn * y.re.y));
         }
 }
 
-// ---- row pass: both half-transforms of one intermediate row, interleaved 128-bit stores -----------
+// ---- row pass: persistent, both half-transforms of one intermediate row per iteration ---------------
 template <int L, bool INV>
-__global__ void __launch_bounds__(L / 8) focus_row_kernel(const FocusParams p) {
+__global__ void __launch_bounds__(L / 16) focus_row_kernel(const FocusParams p) {
     using G = Geo<L>;
-    constexpr int NT = G::NT, NTH = 2 * NT, R3 = G::R3, GI = 2048 / L;
-    extern __shared__ __align__(16) float2 smem[];
-    const int tid = threadIdx.x;
-    const int f = tid / NT, t = tid - f * NT;
-    const int r = blockIdx.x;               // intermediate row (compact)
-    const int phase = p.phase0 + blockIdx.y;
-    const float2* __restrict__ src = p.tmp + (long long)blockIdx.y * L * L + (long long)r * L;
-    float2 v[16];
-#pragma unroll
-    for (int n = 0; n < 16; ++n) v[n] = __ldg(src + n * NT + t);
-    if (f) {
-#pragma unroll
-        for (int n = 0; n < 16; ++n) {
-            float2 w = __ldg(p.tw + n * NT + t);
-            if (INV) w.y = -w.y;
-            v[n] = fcmul(v[n], w);
+    constexpr int NT = G::NT, R3 = G::R3, GI = G::GI;
+    constexpr uint32_t ROW_BYTES = L * sizeof(float2);
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float4* S = reinterpret_cast<float4*>(smraw);                // SBUF exchange
+    float2* inb = reinterpret_cast<float2*>(S + G::SBUF);        // L-element input row
+    uint64_t* bar = reinterpret_cast<uint64_t*>(inb + L);        // 1 mbarrier
+    const int t = threadIdx.x;
+    int r = blockIdx.x;
+    if (t == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        if (r < p.nrows) {
+            mbar_expect_tx(bar, ROW_BYTES);
+            bulk_g2s(inb, p.tmp + (long long)r * L, ROW_BYTES, bar);
         }
     }
-    fft_two_stages<L, INV, 2>(v, t, smem + f * G::SBUF, p.tw, SyncNamed{1 + f, NT});
     __syncthreads();
-    // merged last stage: thread owns items i = tid + g*NTH of BOTH halves -> adjacent outputs 2j, 2j+1
-#pragma unroll
-    for (int g = 0; g < GI; ++g)
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int n = 0; n < R3; ++n) v[(g * 2 + h) * R3 + n] = smem[h * G::SBUF + pad16(n * 256 + tid + g * NTH)];
-#pragma unroll
-    for (int q = 0; q < 2 * GI; ++q) dftR<R3, INV>(v + q * R3);
-    const float sgn = ((tid & 1) ? -1.0f : 1.0f) * p.scale;
-    const int orow = (2 * r + phase + L) & (2 * L - 1);      // fftshift along y
-    if (p.out_kind == PB_OUT_COMPLEX) {
-        float4* __restrict__ dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(p.out) + (long long)orow * p.out_ld);
-#pragma unroll
-        for (int g = 0; g < GI; ++g)
-#pragma unroll
-            for (int kk = 0; kk < R3; ++kk) {
-                const int j = tid + g * NTH + 256 * kk;
-                const float2 A = v[(g * 2 + 0) * R3 + kk], B = v[(g * 2 + 1) * R3 + kk];
-                // U[2j] = (-1)^j A,  U[2j+1] = (-1)^j (-dir*i) B ; fftshift along x: pair index (j + L/2) mod L
-                const float2 Bm = INV ? make_float2(B.y, -B.x) : make_float2(-B.y, B.x);
-                __stcs(dst + ((j + L / 2) & (L - 1)), make_float4(sgn * A.x, sgn * A.y, sgn * Bm.x, sgn * Bm.y));
+    const float sgn = ((t & 1) ? -1.0f : 1.0f) * p.scale;
+    for (int it = 0; r < p.nrows; ++it, r += gridDim.x) {
+        P2 v[16];
+        mbar_wait(bar, it & 1);
+        {
+            const float2* __restrict__ row = inb + t;
+#define PB_X(n) row[(n) * NT]
+            PB_MAKE_LANES_16(v, INV, PB_X)
+#undef PB_X
+        }
+        const int rn = r + gridDim.x;
+        auto sync_and_prefetch = [&]() {
+            __syncthreads();  // every thread holds its inputs in registers: the row buffer is free
+            if (t == 0 && rn < p.nrows) {
+                mbar_expect_tx(bar, ROW_BYTES);
+                bulk_g2s(inb, p.tmp + (long long)rn * L, ROW_BYTES, bar);
             }
-    } else {
-        float2* __restrict__ dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + (long long)orow * p.out_ld);
-        const float s2 = p.scale * p.scale;
+        };
+        fft_two_stages<L, INV, false>(v, t, S, p.plan, sync_and_prefetch, SyncCta());
+        fft_last_stage_load<L, INV>(v, t, S);
+        __syncthreads();  // exchange buffer is free for the next row
 #pragma unroll
-        for (int g = 0; g < GI; ++g)
+        for (int g = 0; g < GI; ++g) dftR<R3, INV>(v + g * R3);
+        const int phs = r / L, rr = r - phs * L;
+        const int orow = (2 * rr + phs + L) & (2 * L - 1);  // fftshift along y
+        if (p.out_kind == PB_OUT_COMPLEX) {
+            float4* __restrict__ dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(p.out) + (long long)orow * p.out_ld);
 #pragma unroll
-            for (int kk = 0; kk < R3; ++kk) {
-                const int j = tid + g * NTH + 256 * kk;
-                const float2 A = v[(g * 2 + 0) * R3 + kk], B = v[(g * 2 + 1) * R3 + kk];
-                float2 I = make_float2(s2 * (A.x * A.x + A.y * A.y), s2 * (B.x * B.x + B.y * B.y));
-                float2* q = dst + ((j + L / 2) & (L - 1));
-                if (p.out_kind == PB_OUT_ACCUMULATE) {
-                    const float2 old = *q;
-                    I = make_float2(fmaf(p.weight, I.x, old.x), fmaf(p.weight, I.y, old.y));
+            for (int g = 0; g < GI; ++g)
+#pragma unroll
+                for (int kk = 0; kk < R3; ++kk) {
+                    const int j = t + g * NT + 256 * kk;
+                    const P2 y = v[g * R3 + kk];
+                    // U[2j] = (-1)^j A,  U[2j+1] = (-1)^j (-dir*i) B ; fftshift along x: pair index (j + L/2) mod L
+                    const float4 o = INV ? make_float4(sgn * y.re.x, sgn * y.im.x, sgn * y.im.y, -sgn * y.re.y)
+                                         : make_float4(sgn * y.re.x, sgn * y.im.x, -sgn * y.im.y, sgn * y.re.y);
+                    st_stream(dst + ((j + L / 2) & (L - 1)), o);
                 }
-                *q = I;
-            }
+        } else {
+            float2* __restrict__ dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + (long long)orow * p.out_ld);
+            const float2 s2 = make_float2(p.scale * p.scale, p.scale * p.scale);
+            const float2 wgt = make_float2(p.weight, p.weight);
+#pragma unroll
+            for (int g = 0; g < GI; ++g)
+#pragma unroll
+                for (int kk = 0; kk < R3; ++kk) {
+                    const int j = t + g * NT + 256 * kk;
+                    const P2 y = v[g * R3 + kk];
+                    float2 I = __fmul2_rn(s2, __ffma2_rn(y.re, y.re, __fmul2_rn(y.im, y.im)));
+                    float2* q = dst + ((j + L / 2) & (L - 1));
+                    if (p.out_kind == PB_OUT_ACCUMULATE) I = __ffma2_rn(wgt, I, *q);
+                    *q = I;
+                }
+        }
     }
+}
+
+// plan table, see Geo<L>
+template <int L>
+int get_focus_plan(Handle* h, const float4** out) {
+    using G = Geo<L>;
+    TwKey key{L, PB_C64, 11};
+    auto it = h->tables.find(key);
+    if (it != h->tables.end()) { *out = reinterpret_cast<const float4*>(it->second); return PB_OK; }
+    auto w = [&](long long num, long long den) {  // exp(-2 pi i num/den), argument reduced exactly
+        num %= den;
+        const double a = -2.0 * 3.14159265358979323846 * (double)num / (double)den;
+        return std::complex<double>(cos(a), sin(a));
+    };
+    std::vector<float4> tab(G::PLAN);
+    for (int k = 0; k < 16; ++k)
+        for (int t = 0; t < G::NT; ++t) {
+            const std::complex<double> a = w((long long)t * k, L), b = w((long long)t * (2 * k + 1), 2 * L);
+            tab[G::TW1 + k * G::NT + t] = make_float4((float)a.real(), (float)b.real(), (float)a.imag(), (float)b.imag());
+        }
+    for (int k = 1; k < 16; ++k)
+        for (int m = 0; m < G::NT / 16; ++m) {
+            const std::complex<double> a = w(16LL * m * k, L);
+            tab[G::TW2 + (k - 1) * (G::NT / 16) + m] = make_float4((float)a.real(), (float)a.real(), (float)a.imag(), (float)a.imag());
+        }
+    void* d = nullptr;
+    PB_CUDA(h, cudaMalloc(&d, tab.size() * sizeof(float4)));
+    PB_CUDA(h, cudaMemcpy(d, tab.data(), tab.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    h->tables[key] = d;
+    *out = reinterpret_cast<const float4*>(d);
+    return PB_OK;
 }
 
 template <int L, bool INV>
 int launch_focus(Handle* h, FocusParams p, cudaStream_t st) {
     using G = Geo<L>;
     constexpr int T = 4;
-    const size_t smem_col = (size_t)T * (G::SBUF + 4) * sizeof(float2);
-    const size_t smem_row = (size_t)2 * G::SBUF * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
+    const size_t smem_col = (size_t)(T * (G::SBUF + 2) + G::PLAN) * sizeof(float4) + 2 * sizeof(uint64_t);
+    const size_t smem_row = (size_t)G::SBUF * sizeof(float4) + (size_t)L * sizeof(float2) + 2 * sizeof(uint64_t);
+    static int row_ctas = 0;
+    if (!row_ctas) {
         PB_CUDA(h, cudaFuncSetAttribute(focus_col_kernel<L, INV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
         PB_CUDA(h, cudaFuncSetAttribute(focus_row_kernel<L, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
-        attr_done = true;
+        int n = 0;
+        PB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, focus_row_kernel<L, INV>, L / 16, smem_row));
+        n = n > 0 ? n : 1;
+        // Keep >= 64 KB of the unified L1/shared array as L1: the 34 KB twiddle plan is re-read by every
+        // line and must hit there.  (Left to itself the driver picks the 228 KB carve-out and the plan
+        // streams from L2 at ~300 cycles a load.)
+        const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
+        const int by_l1 = std::max(1, (int)((unified - l1_keep) / (smem_row + 1024)));
+        n = std::min(n, by_l1);
+        if (const char* e = getenv("PB_ROW_CTAS_PER_SM")) n = std::max(1, atoi(e));
+        row_ctas = n;
+        auto carve = [&](size_t bytes) { return (int)std::min<size_t>(100, (bytes * 100 + h->max_smem_optin - 1) / h->max_smem_optin); };
+        int row_pct = carve((size_t)n * (smem_row + 1024)), col_pct = carve(smem_col + 1024);
+        if (const char* e = getenv("PB_CARVEOUT_PCT")) row_pct = col_pct = atoi(e);
+        PB_CUDA(h, cudaFuncSetAttribute(focus_row_kernel<L, INV>, cudaFuncAttributePreferredSharedMemoryCarveout, row_pct));
+        PB_CUDA(h, cudaFuncSetAttribute(focus_col_kernel<L, INV, T>, cudaFuncAttributePreferredSharedMemoryCarveout, col_pct));
     }
-    static const int mode = [] { const char* e = getenv("PB_FOCUS_PHASES_PER_LAUNCH"); return e ? atoi(e) : 1; }();
-    if (mode == 2) {  // both phases per launch: 2 launches, 2*N*N intermediate
-        p.phase0 = 0;
-        focus_col_kernel<L, INV, T><<<dim3(L / T, 2), T * G::NT, smem_col, st>>>(p);
-        PB_LAUNCH_CHECK(h);
-        focus_row_kernel<L, INV><<<dim3(L, 2), L / 8, smem_row, st>>>(p);
-        PB_LAUNCH_CHECK(h);
-    } else {          // one phase at a time: 4 launches, N*N intermediate stays in L2
-        for (int ph = 0; ph < 2; ++ph) {
-            p.phase0 = ph;
-            focus_col_kernel<L, INV, T><<<dim3(L / T, 1), T * G::NT, smem_col, st>>>(p);
-            PB_LAUNCH_CHECK(h);
-            focus_row_kernel<L, INV><<<dim3(L, 1), L / 8, smem_row, st>>>(p);
-            PB_LAUNCH_CHECK(h);
-        }
-    }
+    PB_TRY(get_focus_plan<L>(h, &p.plan));
+    p.nrows = 2 * L;
+    focus_col_kernel<L, INV, T><<<L / T, T * G::NT, smem_col, st>>>(p);
+    PB_LAUNCH_CHECK(h);
+    focus_row_kernel<L, INV><<<std::min(h->sm_count * row_ctas, p.nrows), L / 16, smem_row, st>>>(p);
+    PB_LAUNCH_CHECK(h);
     return PB_OK;
 }
 
@@ -331,11 +491,9 @@ int try_tuned_fft2(Handle* h, int dtype, const void* in, int in_kind, const void
     void* tmp = nullptr;
     PB_TRY(ensure_scratch(h, 0, (size_t)2 * N * N * sizeof(float2), &tmp));
     p.tmp = reinterpret_cast<float2*>(tmp);
-    const void* tw = nullptr;
-    PB_TRY(get_twiddles(h, 2 * N, PB_C64, &tw));
-    p.tw = reinterpret_cast<const float2*>(tw);
+    p.plan = nullptr;
     p.out = out; p.out_ld = out_ld; p.out_kind = out_kind; p.scale = (float)scale; p.weight = (float)weight;
-    p.phase0 = 0;
+    p.nrows = 0;
     if (dir < 0) {
         if (N == 512) return launch_focus<512, false>(h, p, st);
         if (N == 1024) return launch_focus<1024, false>(h, p, st);
