@@ -139,6 +139,20 @@ int pb_mdft_apply(pb_handle_t h, int dtype, const void* Ey, const void* Ex, int 
                   int left_first, void* work, void* stream);
 long long pb_mdft_work_elems(int my, int ny, int mx, int nx, int adjoint, int left_first);
 
+/* ---- matrix DFT on the tcgen05 tensor cores (complex64, forward) -------------------------
+ * 3xTF32 split (fp32-accurate) real embedding of the complex product; see csrc/mdft_tc.cu.
+ *   pb_mdft_tc_supported : 1 when (my, ny, mx, nx) is covered (multiples of 128 / 128 / 128 / 16)
+ *   pb_mdft_tc_expand    : complex basis E (m,n) -> real expansions hi, lo, each (2m, 2n) fp32;
+ *                          done once per executor for Ex and for Ey (prysm/fttools.py:187-191)
+ *   pb_mdft_tc_apply     : out(my,mx) = norm * Ey @ a @ Ex^T   (prysm/fttools.py:201-207);
+ *                          work: pb_mdft_tc_work_bytes() bytes of 1 KB-aligned device scratch */
+int pb_mdft_tc_supported(int my, int ny, int mx, int nx);
+int pb_mdft_tc_expand(pb_handle_t h, const void* E, int m, int n, void* hi, void* lo, void* stream);
+long long pb_mdft_tc_work_bytes(int my, int ny, int mx, int nx);
+int pb_mdft_tc_apply(pb_handle_t h, const void* ExB_hi, const void* ExB_lo, const void* EyB_hi,
+                     const void* EyB_lo, int my, int ny, int mx, int nx, const void* a, void* out,
+                     double norm, void* work, void* stream);
+
 /* ---- elementwise / reductions -----------------------------------------------------------
  * out = amp * exp(i*kscale*opd)   (amp optional).  prysm/propagation/wavefront.py:59-96 */
 int pb_phase_screen(pb_handle_t h, int dtype, const void* amp, int amp_kind, const void* opd,

@@ -34,6 +34,10 @@ SIGNATURES = {
     'pb_cgemm': (_i, [_vp, _i, _i, _i, _i, _i, _i, _d, _vp, _ll, _vp, _ll, _vp, _ll, _vp]),
     'pb_mdft_apply': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _d, _i, _i, _vp, _vp]),
     'pb_mdft_work_elems': (_ll, [_i, _i, _i, _i, _i, _i]),
+    'pb_mdft_tc_supported': (_i, [_i, _i, _i, _i]),
+    'pb_mdft_tc_expand': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    'pb_mdft_tc_work_bytes': (_ll, [_i, _i, _i, _i]),
+    'pb_mdft_tc_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _d, _vp, _vp]),
     'pb_phase_screen': (_i, [_vp, _i, _vp, _i, _vp, _d, _ll, _vp, _vp]),
     'pb_intensity': (_i, [_vp, _i, _vp, _ll, _d, _i, _vp, _vp]),
     'pb_binary': (_i, [_vp, _i, _i, _vp, _vp, _d, _d, _i, _ll, _vp, _vp]),

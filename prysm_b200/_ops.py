@@ -219,6 +219,34 @@ def mdft_apply(Ey, Ex, a, norm, adjoint, left_first):
     return out
 
 
+def mdft_tc_supported(my, ny, mx, nx):
+    return bool(lib.pb_mdft_tc_supported(my, ny, mx, nx))
+
+
+def mdft_tc_expand(E):
+    """complex64 basis (m, n) -> TF32-split real expansions (hi, lo), each (2m, 2n) float32."""
+    m, n = E.shape
+    hi = torch.empty((2 * m, 2 * n), dtype=torch.float32, device=E.device)
+    lo = torch.empty_like(hi)
+    h, st = _ctx(E)
+    h.check(lib.pb_mdft_tc_expand(h.ptr, _p(E), m, n, _p(hi), _p(lo), st))
+    return hi, lo
+
+
+def mdft_tc_apply(ex_hi, ex_lo, ey_hi, ey_lo, a, norm):
+    my, ny = ey_hi.shape[0] // 2, ey_hi.shape[1] // 2
+    mx, nx = ex_hi.shape[0] // 2, ex_hi.shape[1] // 2
+    a = a.contiguous()
+    if tuple(a.shape) != (ny, nx):
+        raise ValueError(f'array of shape {tuple(a.shape)} does not match the executor ({(ny, nx)})')
+    out = torch.empty((my, mx), dtype=torch.complex64, device=a.device)
+    work = torch.empty(lib.pb_mdft_tc_work_bytes(my, ny, mx, nx), dtype=torch.uint8, device=a.device)
+    h, st = _ctx(a)
+    h.check(lib.pb_mdft_tc_apply(h.ptr, _p(ex_hi), _p(ex_lo), _p(ey_hi), _p(ey_lo), my, ny, mx, nx, _p(a), _p(out),
+                                 float(norm), _p(work), st))
+    return out
+
+
 def phase_screen(amp, opd, kscale):
     opd = opd.contiguous()
     if opd.dtype not in _CPLX_OF:

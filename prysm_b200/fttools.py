@@ -93,7 +93,7 @@ class MDFT:
     (prysm/fttools.py:155-232).  complex64 runs on the tcgen05 tensor cores when the shape
     allows, otherwise (and always for complex128) on the fp32 / fp64 CUDA-core GEMM."""
 
-    def __init__(self, x, y, fx, fy, sign=-1, norm=1.0):
+    def __init__(self, x, y, fx, fy, sign=-1, norm=1.0, use_tensor_cores=True):
         x, y, fx, fy = _host(x), _host(y), _host(fx), _host(fy)
         cd = config.complex_dtype
         dev = _ops.device()
@@ -103,10 +103,16 @@ class MDFT:
         Nx, Ny, Mx, My = len(x), len(y), len(fx), len(fy)
         self._forward_left_first = My * Nx * (Ny + Mx) <= Ny * Mx * (Nx + My)
         self._adjoint_left_first = Ny * Mx * (My + Nx) <= My * Nx * (Mx + Ny)
+        # tensor-core plan: TF32-split real expansions of both bases, built once (4x the basis bytes)
+        self._tc = None
+        if cd == torch.complex64 and use_tensor_cores and _ops.mdft_tc_supported(My, Ny, Mx, Nx):
+            self._tc = _ops.mdft_tc_expand(self.Ex) + _ops.mdft_tc_expand(self.Ey)
 
     def __call__(self, ary):
-        return _ops.mdft_apply(self.Ey, self.Ex, _prep(ary, self.Ey.dtype), self.norm, False,
-                               self._forward_left_first)
+        ary = _prep(ary, self.Ey.dtype)
+        if self._tc is not None:
+            return _ops.mdft_tc_apply(*self._tc, ary, self.norm)
+        return _ops.mdft_apply(self.Ey, self.Ex, ary, self.norm, False, self._forward_left_first)
 
     def adjoint(self, grad):
         return _ops.mdft_apply(self.Ey, self.Ex, _prep(grad, self.Ey.dtype), self.norm, True,

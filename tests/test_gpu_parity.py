@@ -440,3 +440,26 @@ def test_polychromatic_recipe_small(pb):
     total = pb.polynomials.sum_of_2d_modes(torch.stack(planes), wts)
     assert rel_linf(host(total), ref) < 2 * TOL32
     pb.config.precision = 64
+
+
+# ------------------------------------------------------------------------------------------
+# tensor-core matrix DFT against the CUDA-core GEMM and the oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('N,M', [(256, 128), (512, 256), (1024, 128)])
+def test_mdft_tensor_core_path(pb, N, M):
+    F = pb.fttools
+    pb.config.precision = 32
+    rng = np.random.default_rng(N + M)
+    x = (np.arange(N) - N // 2) * 0.1
+    f = (np.arange(M) - M // 2) * (0.37 / (N * 0.1))
+    a = (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))).astype(np.complex64)
+    ref = O.MDFT(x, x, f, f, -1, 0.5)(a.astype(np.complex128))
+    tc = F.MDFT(x, x, f, f, -1, 0.5)
+    assert tc._tc is not None, 'tensor-core plan should cover this shape'
+    simt = F.MDFT(x, x, f, f, -1, 0.5, use_tensor_cores=False)
+    assert simt._tc is None
+    assert rel_linf(host(tc(a)), ref) < 1.5 * TOL32          # 3xTF32 + chunked fp32 accumulation
+    assert rel_linf(host(simt(a)), ref) < TOL32
+    # ragged shapes fall back to the CUDA-core GEMM
+    assert F.MDFT(x[:100], x[:100], f[:50], f[:50])._tc is None
+    pb.config.precision = 64
