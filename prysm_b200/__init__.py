@@ -12,7 +12,8 @@ of include/prysm_b200.h).  Importing this package without the built library rais
 """
 from . import _capi  # noqa: F401  (fails loudly if the CUDA library is missing)
 from .conf import config  # noqa: F401
-from . import fttools, propagation, otf, psf, polynomials  # noqa: F401
+from . import fttools, propagation, otf, psf, polynomials, polychromatic, mathops  # noqa: F401
+from ._capi import B200Error  # noqa: F401
 from .propagation import Wavefront  # noqa: F401
 from ._ops import asdevice, asnumpy, set_device  # noqa: F401
 

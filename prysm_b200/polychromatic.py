@@ -1,0 +1,95 @@
+"""Incoherent (polychromatic / multi-field) sums sharded over GPUs.
+
+The reference has no multi-device code: its documented recipe is a Python loop over wavelengths
+followed by `sum_of_2d_modes(stack, weights)` (docs/source/how-tos/Polychromatic Propagation.ipynb:86-98,
+prysm/polynomials/fitting.py:37), and its docs advise users to parallelise that loop themselves.
+Here the loop is the sharded unit of work:
+
+    rank r of W takes units r, r+W, r+2W, ...         (no data-path communication)
+    each unit's |field|^2 is accumulated, weighted, into ONE local fp32/fp64 plane as it is produced
+    one sum-reduce of that plane (NCCL over NVLink when W > 1) gives the total on `dst` (or on all ranks)
+
+A single 2-D field is never split across devices.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _ops
+from . import propagation as P
+from .conf import config
+
+
+def shard_units(n_units, rank, world):
+    """Indices of the units owned by `rank`: round-robin, so equal-cost units balance to within one."""
+    if not (0 <= rank < world):
+        raise ValueError(f'rank {rank} outside world of {world}')
+    return list(range(rank, n_units, world))
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def sharded_incoherent_sum(n_units, accumulate_unit, plane, group=None, dst=None):
+    """Generic driver.  `accumulate_unit(i, plane)` must add unit i's weighted intensity into `plane`
+    (a tensor on this rank's device).  After the local loop the planes are summed across ranks:
+    onto `dst` if given (other ranks' planes are left as their partial sums), else onto every rank."""
+    rank, world = _world(group)
+    for i in shard_units(n_units, rank, world):
+        accumulate_unit(i, plane)
+    if world > 1:
+        if dst is None:
+            dist.all_reduce(plane, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(plane, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return plane
+
+
+def polychromatic_psf(amplitude, phase, wavelengths, weights, dx, efl, focal_dx, focal_samples, kind='czt',
+                      shift=(0, 0), group=None, dst=None):
+    """Weighted incoherent PSF over `wavelengths` on a common focal grid.
+
+    Per wavelength (exactly the reference recipe): from_amp_and_phase -> prepare_executor(kind) ->
+    focus_dft -> intensity; the weighted sum is accumulated as the planes are produced.  Returns the
+    (focal_samples, focal_samples) real plane; with torch.distributed initialised the wavelengths are
+    sharded over the ranks and the result is reduced (see sharded_incoherent_sum)."""
+    amp = None if amplitude is None else _ops.asdevice(amplitude)
+    opd = _ops.asdevice(phase)
+    if opd.dtype not in (torch.float32, torch.float64):
+        opd = opd.to(config.real_dtype)
+    wavelengths = np.asarray(wavelengths, dtype=np.float64)
+    weights = np.asarray(weights, dtype=np.float64)
+    if wavelengths.shape != weights.shape:
+        raise ValueError('one weight per wavelength is required')
+    if isinstance(focal_samples, int):
+        focal_samples = (focal_samples, focal_samples)
+    plane = torch.zeros(tuple(focal_samples), dtype=opd.dtype, device=opd.device)
+
+    def unit(i, acc):
+        wf = P.Wavefront.from_amp_and_phase(amp, opd, float(wavelengths[i]), dx)
+        ex = wf.prepare_executor(efl, focal_dx, focal_samples, shift=shift, kind=kind)
+        field = wf.focus_dft(ex).data
+        _ops.intensity(field, weight=float(weights[i]), out=acc)
+
+    return sharded_incoherent_sum(len(wavelengths), unit, plane, group=group, dst=dst)
+
+
+def polychromatic_psf_fft(amplitude, phase, wavelengths, weights, Q=2, group=None, dst=None):
+    """Same sum on each wavelength's own FFT grid (`Wavefront.focus(Q)`): the synthesis, the padded FFT
+    and the weighted |.|^2 accumulate are one fused call per wavelength (no complex field is written)."""
+    amp = None if amplitude is None else _ops.asdevice(amplitude)
+    opd = _ops.asdevice(phase)
+    if opd.dtype not in (torch.float32, torch.float64):
+        opd = opd.to(config.real_dtype)
+    wavelengths = np.asarray(wavelengths, dtype=np.float64)
+    weights = np.asarray(weights, dtype=np.float64)
+    ky, kx = P._padded_shape(opd.shape, Q)
+    plane = torch.zeros((ky, kx), dtype=opd.dtype, device=opd.device)
+
+    def unit(i, acc):
+        P.psf_from_amp_and_phase(amp, opd, float(wavelengths[i]), Q, weight=float(weights[i]), out=acc)
+
+    return sharded_incoherent_sum(len(wavelengths), unit, plane, group=group, dst=dst)

@@ -1,0 +1,43 @@
+"""CPU: set_backend_to_b200() re-binds prysm's hot-path names and set_backend_to_defaults() restores them.
+Runs only where an unmodified prysm is importable (this container: /root/reference); the GPU box has no prysm."""
+import os
+import sys
+
+import pytest
+
+REF = os.environ.get('PRYSM_REFERENCE', '/root/reference')
+
+
+@pytest.fixture()
+def prysm_pkg():
+    if not os.path.isdir(os.path.join(REF, 'prysm')):
+        pytest.skip('reference prysm not present on this box')
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    try:
+        import prysm.propagation  # noqa: F401
+        import prysm
+        yield prysm
+    finally:
+        sys.path.remove(REF)
+
+
+def test_rebinding_round_trip(prysm_pkg):
+    import prysm.propagation as pp
+    import prysm.propagation.wavefront as pw
+    import prysm.fttools as pf
+    import prysm.otf as po
+    from prysm_b200 import mathops, propagation as bp, fttools as bf, otf as bo
+    orig = (pp.focus, pw.focus, pw.angular_spectrum, pf.MDFT, po.mtf_from_psf, pw.prepare_executor)
+    names = mathops.set_backend_to_b200()
+    try:
+        assert ('prysm.propagation.wavefront', 'focus') in names
+        assert pp.focus is bp.focus and pw.focus is bp.focus            # Wavefront.focus resolves this global
+        assert pw.angular_spectrum is bp.angular_spectrum and pw.prepare_executor is bp.prepare_executor
+        assert pf.MDFT is bf.MDFT and po.mtf_from_psf is bo.mtf_from_psf
+        import prysm.propagation.dft as pd
+        assert pd.MDFT is bf.MDFT and pd.CZT is bf.CZT                  # prepare_executor's constructors
+    finally:
+        mathops.set_backend_to_defaults()
+    assert (pp.focus, pw.focus, pw.angular_spectrum, pf.MDFT, po.mtf_from_psf, pw.prepare_executor) == orig
+    assert mathops._saved == {}
