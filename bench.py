@@ -131,6 +131,37 @@ def cpu_focus_rate(seconds_budget, workers, pupils):
     return done / t_total, done, t_total
 
 
+def measure_mdft_c3(pb, peaks):
+    """BASELINE configs[2]: 4096^2 -> 512^2 fixed-sampling focus via MDFT on the tcgen05 tensor cores.
+    Algorithmic flops: 8*(My*Ny*Nx + My*Nx*Mx) = 77 309 411 328 per apply."""
+    import torch
+    from prysm_b200 import propagation as P
+    n, m = 4096, 512
+    gen = torch.Generator(device='cuda').manual_seed(7)
+    a = torch.complex(torch.randn((n, n), generator=gen, device='cuda'), torch.randn((n, n), generator=gen, device='cuda'))
+    ex = P.prepare_executor(10.0 / n, (n, n), HENE * 10.0 / 4, (m, m), HENE, EFL, kind='mdft')
+    for _ in range(3):
+        ex(a)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        ex(a)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / reps
+    flops = 8 * (m * n * n + m * n * m)
+    peak = float(peaks.get('bf16_tflops', 1590.0))
+    ach = flops / sec / 1e12
+    return {'workload': 'C3: 4096x4096 complex64 -> 512x512 focus_dft(MDFT), 3xTF32 tcgen05 complex GEMM',
+            'us_per_apply': sec * 1e6, 'applies_per_s': 1.0 / sec, 'tensor_core_path': ex._tc is not None,
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                         'traffic': None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (measured, burst)',
+                         'algorithmic_flops_per_apply': flops, 'issued_tf32_tflops': 3 * ach,
+                         'note': 'algorithmic flops vs the bf16 peak; the path issues 3 TF32 MMAs per product (TF32 runs at half the bf16 rate)'}}
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm (oracle port: numpy + scipy.fft pocketfft, the same
     third-party FFT the reference calls) on this box's host cores, all threads, same config/metric."""
@@ -294,6 +325,8 @@ def run_b200(args):
         }
         if cpu is not None:
             line['cpu_baseline'] = cpu
+        if world == 1:
+            line['mdft_c3'] = measure_mdft_c3(pb, peaks)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -178,6 +178,10 @@ int pb_weighted_sum(pb_handle_t h, int dtype, const void* modes, int k, long lon
  * prysm/otf.py:62-202 */
 int pb_otf_normalize(pb_handle_t h, int dtype, const void* D, int ny, int nx, int which,
                      void* mtf, void* ptf, void* otf, void* stream);
+/* Baliga-Cohn encircled energy of a real MTF array (ny,nx) with frequency spacing df [cy/mm] at nr radii
+ * [mm] (HOST arrays in/out; synchronises the stream).  prysm/otf.py:319-414 */
+int pb_encircled_energy(pb_handle_t h, int dtype, const void* mtf, int ny, int nx, double df,
+                        const double* radii_mm_host, int nr, double* out_host, void* stream);
 /* moments of a real array: sums_host[0..2] = sum(d), sum(d*y), sum(d*x) (HOST doubles; this call
  * synchronises the stream).  prysm/psf.py:174-203 */
 int pb_moments(pb_handle_t h, int dtype, const void* data, int ny, int nx, double* sums_host,

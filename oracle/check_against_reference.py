@@ -112,6 +112,7 @@ for prec, rdt, cdt, eps in ((64, np.float64, np.complex128, 1e-13), (32, np.floa
     check(tag + 'ptf', O.ptf_from_psf(p, 1.5)[0], otf.ptf_from_psf(p, 1.5).data)
     check(tag + 'otf', O.otf_from_psf(p, 1.5)[0], otf.otf_from_psf(p, 1.5).data)
     assert O.mtf_from_psf(p, 1.5)[1] == otf.mtf_from_psf(p, 1.5).dx
+    check(tag + 'encircled_energy', O.encircled_energy(p, 1.5, [2.0, 7.5]), otf.encircled_energy(p, 1.5, [2.0, 7.5]), 1e-6 if prec == 32 else 1e-13)
     # reductions
     modes = rng.random((5, 8, 9)).astype(rdt)
     wts = rng.random(5).astype(rdt)

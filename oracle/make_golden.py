@@ -74,6 +74,8 @@ def small():
     g['wf_mtf'], g['wf_mtf_df'] = mt.data, np.float64(mt.dx)
     g['wf_ptf'] = otf.ptf_from_psf(psfwf.intensity).data
     g['wf_otf'] = otf.otf_from_psf(psfwf.intensity).data
+    g['wf_ee_radii'] = np.array([1.0, 5.0, 12.5, 40.0])
+    g['wf_ee'] = otf.encircled_energy(psfwf.intensity.data, psfwf.dx, g['wf_ee_radii'])
     g['wf_centroid'] = np.asarray(psf.centroid(psfwf.intensity.data, psfwf.dx))
     g['wf_centroid_px'] = np.asarray(psf.centroid(psfwf.intensity.data, unit='pixels'))
     x, y = make_xy_grid(64, diameter=10.0)

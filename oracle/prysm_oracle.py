@@ -501,6 +501,20 @@ def otf_from_psf(psf, dx):
     return n, df
 
 
+def encircled_energy(psf, dx, radius):
+    """Baliga & Cohn: r * sum(MTF * J1(2 pi r nu)/nu) * dnu^2, nu on the fftrange*df grid with nu(0) -> 1e-16;
+    radius in um -> mm.  prysm/otf.py:319-414."""
+    from scipy.special import j1
+    mtf, df = mtf_from_psf(psf, dx)
+    fy = fftrange(mtf.shape[0]) * df
+    fx = fftrange(mtf.shape[1]) * df
+    nu = np.hypot(*np.meshgrid(fx, fy))
+    nu[nu == 0] = 1e-16
+    radii = np.atleast_1d(np.asarray(radius, dtype=np.float64)) / 1e3
+    out = np.array([r * (mtf * j1(2 * np.pi * r * nu) / nu).sum() * df * df for r in radii])
+    return float(out[0]) if np.ndim(radius) == 0 else out
+
+
 def sum_of_2d_modes(modes, weights):
     """tensordot over the leading axis.  prysm/polynomials/fitting.py:7-37."""
     modes = np.asarray(modes)

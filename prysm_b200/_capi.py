@@ -44,6 +44,7 @@ SIGNATURES = {
     'pb_mul_outer': (_i, [_vp, _i, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _d, _vp, _ll, _vp]),
     'pb_weighted_sum': (_i, [_vp, _i, _vp, _i, _ll, C.POINTER(_d), _vp, _vp]),
     'pb_otf_normalize': (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'pb_encircled_energy': (_i, [_vp, _i, _vp, _i, _i, _d, C.POINTER(_d), _i, C.POINTER(_d), _vp]),
     'pb_moments': (_i, [_vp, _i, _vp, _i, _i, C.POINTER(_d), _vp]),
 }
 

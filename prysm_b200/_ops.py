@@ -329,6 +329,16 @@ def otf_normalize(D, which):
     return mtf, ptf, otf
 
 
+def encircled_energy(mtf, df, radii_mm):
+    mtf = mtf.contiguous()
+    ny, nx = mtf.shape
+    r, rp = _darr(radii_mm)
+    out = (C.c_double * len(r))()
+    h, st = _ctx(mtf)
+    h.check(lib.pb_encircled_energy(h.ptr, _CODE[mtf.dtype], _p(mtf), ny, nx, float(df), rp, len(r), out, st))
+    return np.array(out[:])
+
+
 def moments(data):
     data = data.contiguous()
     if data.dtype not in _CPLX_OF:

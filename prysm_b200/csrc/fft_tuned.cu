@@ -192,16 +192,29 @@ template <int L> struct Geo {
 // First two radix-16 stages on both lanes.  In: v[n] = lanes of x[n*NT + t].  Out: stage-2 results in S
 // (float4, 1-in-16 padded, position-major): final-stage item i in [0, 256) reads S[pad16(n*256 + i)],
 // n < L/256, and after the radix-(L/256) dft holds X[i + 256*k].
-template <int L, bool INV, bool PLAN_SMEM, class Sync1, class Sync>
+// Twiddle sources: 0 = float4 plan in global memory (L1 evict_last), 1 = float4 plan in shared memory,
+// 2 = "plain" float2 tables in global memory, the same twiddle for both lanes (k = 1..15 only).
+template <int KIND> __device__ __forceinline__ float4 load_tw(const void* base, int idx) {
+    if (KIND == 1) return reinterpret_cast<const float4*>(base)[idx];
+    if (KIND == 0) return ld_plan(reinterpret_cast<const float4*>(base) + idx);
+    float2 w;
+    asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(w.x), "=f"(w.y) : "l"(reinterpret_cast<const float2*>(base) + idx));
+    return make_float4(w.x, w.x, w.y, w.y);
+}
+
+template <int L, bool INV, int KIND, class Sync1, class Sync>
 __device__ __forceinline__ void fft_two_stages(P2 (&v)[16], const int t, float4* __restrict__ S,
-                                               const float4* __restrict__ plan, Sync1 sync1, Sync sync) {
+                                               const void* __restrict__ tw1, const void* __restrict__ tw2, Sync1 sync1,
+                                               Sync sync) {
     using G = Geo<L>;
     constexpr int NT = G::NT;
     dft16<INV>(v);
-    {
-        const float4* __restrict__ w1 = plan + G::TW1 + t;
+    if (KIND == 2) {  // tw1[(k-1)*NT + t]
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = mul_tw<INV>(v[k], PLAN_SMEM ? w1[k * NT] : ld_plan(w1 + k * NT));
+        for (int k = 1; k < 16; ++k) v[k] = mul_tw<INV>(v[k], load_tw<KIND>(tw1, (k - 1) * NT + t));
+    } else {          // tw1[k*NT + t], k = 0 carries lane B's w_2L^t
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = mul_tw<INV>(v[k], load_tw<KIND>(tw1, k * NT + t));
     }
     {
         float4* __restrict__ d = S + t * 17;
@@ -217,11 +230,8 @@ __device__ __forceinline__ void fft_two_stages(P2 (&v)[16], const int t, float4*
     sync();
     dft16<INV>(v);
     const int m = t >> 4, a = t & 15;
-    {
-        const float4* __restrict__ w2 = plan + G::TW2 + m;
 #pragma unroll
-        for (int k = 1; k < 16; ++k) v[k] = mul_tw<INV>(v[k], PLAN_SMEM ? w2[(k - 1) * (NT / 16)] : ld_plan(w2 + (k - 1) * (NT / 16)));
-    }
+    for (int k = 1; k < 16; ++k) v[k] = mul_tw<INV>(v[k], load_tw<KIND>(tw2, (k - 1) * (NT / 16) + m));
     {
         float4* __restrict__ d = S + m * 272 + a;
 #pragma unroll
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(T * L / 16) focus_col_kernel(const FocusParams
 #undef PB_X
     float4* S = smem4 + c * (G::SBUF + 2);  // +2: skews the T buffers across banks
     mbar_wait(bar, 0);
-    fft_two_stages<L, INV, true>(v, t, S, plan_s, SyncCta(), SyncCta());
+    fft_two_stages<L, INV, 1>(v, t, S, plan_s + G::TW1, plan_s + G::TW2, SyncCta(), SyncCta());
     fft_last_stage_load<L, INV>(v, t, S);
 #pragma unroll
     for (int g = 0; g < G::GI; ++g) dftR<G::R3, INV>(v + g * G::R3);
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(L / 16) focus_row_kernel(const FocusParams p) 
                 bulk_g2s(inb, p.tmp + (long long)rn * L, ROW_BYTES, bar);
             }
         };
-        fft_two_stages<L, INV, false>(v, t, S, p.plan, sync_and_prefetch, SyncCta());
+        fft_two_stages<L, INV, 0>(v, t, S, p.plan + G::TW1, p.plan + G::TW2, sync_and_prefetch, SyncCta());
         fft_last_stage_load<L, INV>(v, t, S);
         __syncthreads();  // exchange buffer is free for the next row
 #pragma unroll
@@ -470,9 +480,154 @@ int launch_focus(Handle* h, FocusParams p, cudaStream_t st) {
     return PB_OK;
 }
 
+
+// =====================================================================================================
+// Register-engine version of the generic axis pass (AxisPass semantics, complex64 in/out) for
+// L in {1024, 2048, 4096}: two lines per thread group ride the two packed lanes.  ROWS: one CTA = 2 rows;
+// COLS: one CTA = TP pairs of adjacent columns.  Used by pb_fft2 / pb_axis_dft / pb_angular_spectrum for
+// every power-of-two pass the focus kernels above do not cover (CZT, FFTDFT, free space, psf -> otf).
+// =====================================================================================================
+__device__ __forceinline__ float2 cmul_s(float2 a, float2 b, int conj) {
+    return conj ? make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y))
+                : make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+template <int L, bool INV, bool COLS, int TP>
+__global__ void __launch_bounds__((COLS ? TP : 1) * L / 16) axis_reg_kernel(const AxisPass p, const float2* __restrict__ tw1,
+                                                                            const float2* __restrict__ tw2) {
+    using G = Geo<L>;
+    constexpr int NT = G::NT;
+    extern __shared__ __align__(16) float4 smem4[];
+    const int c = COLS ? threadIdx.x % TP : 0, t = COLS ? threadIdx.x / TP : threadIdx.x;
+    const int b0 = (blockIdx.x * (COLS ? TP : 1) + c) * 2;   // lines b0 (lane A) and b0 + 1 (lane B)
+    const bool hasA = b0 < p.nb, hasB = b0 + 1 < p.nb;
+    const float2* __restrict__ in = reinterpret_cast<const float2*>(p.in);
+    const float2* __restrict__ pre_e = reinterpret_cast<const float2*>(p.pre_e);
+    const float2* __restrict__ pre_b = reinterpret_cast<const float2*>(p.pre_b);
+    float2 pbA = make_float2(1.f, 0.f), pbB = pbA;
+    if (pre_b) { if (hasA) pbA = pre_b[b0]; if (hasB) pbB = pre_b[b0 + 1]; }
+    P2 v[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        const int j = n * NT + t;
+        int pp = j + p.rot_in;
+        if (pp >= L) pp -= L;
+        const int li = pp - p.in_off;
+        float2 xa = make_float2(0.f, 0.f), xb = xa;
+        if (li >= 0 && li < p.n_in) {
+            const long long o = (long long)b0 * p.ibs + (long long)li * p.ies;
+            if (hasA) xa = ld_stream(in + o);
+            if (hasB) xb = ld_stream(in + o + p.ibs);
+            if (pre_e) { const float2 w = pre_e[j - p.pre_off]; xa = cmul_s(xa, w, p.pre_e_conj); xb = cmul_s(xb, w, p.pre_e_conj); }
+            if (pre_b) { xa = cmul_s(xa, pbA, p.pre_b_conj); xb = cmul_s(xb, pbB, p.pre_b_conj); }
+        }
+        v[n] = {make_float2(xa.x, xb.x), make_float2(xa.y, xb.y)};
+    }
+    float4* S = smem4 + c * (G::SBUF + 2);
+    fft_two_stages<L, INV, 2>(v, t, S, tw1, tw2, SyncCta(), SyncCta());
+    fft_last_stage_load<L, INV>(v, t, S);
+#pragma unroll
+    for (int g = 0; g < G::GI; ++g) dftR<G::R3, INV>(v + g * G::R3);
+    const float2* __restrict__ post_e = reinterpret_cast<const float2*>(p.post_e);
+    const float2* __restrict__ post_b = reinterpret_cast<const float2*>(p.post_b);
+    float2 qbA = make_float2(1.f, 0.f), qbB = qbA;
+    if (post_b) { if (hasA) qbA = post_b[b0]; if (hasB) qbB = post_b[b0 + 1]; }
+    const float scale = (float)p.scale;
+    float2* __restrict__ out = reinterpret_cast<float2*>(p.out);
+#pragma unroll
+    for (int g = 0; g < G::GI; ++g)
+#pragma unroll
+        for (int kk = 0; kk < G::R3; ++kk) {
+            const int k = t + g * NT + 256 * kk;
+            int q = k - p.crop_off + p.rot_out;
+            if (q < 0) q += L;
+            if (q >= L) q -= L;
+            if (q >= p.n_out) continue;
+            const P2 y = v[g * G::R3 + kk];
+            float2 ya = make_float2(y.re.x, y.im.x), yb = make_float2(y.re.y, y.im.y);
+            if (post_e) { const float2 w = post_e[k - p.post_off]; ya = cmul_s(ya, w, p.post_e_conj); yb = cmul_s(yb, w, p.post_e_conj); }
+            if (post_b) { ya = cmul_s(ya, qbA, p.post_b_conj); yb = cmul_s(yb, qbB, p.post_b_conj); }
+            const long long o = (long long)b0 * p.obs + (long long)q * p.oes;
+            if (hasA) st_stream(out + o, make_float2(ya.x * scale, ya.y * scale));
+            if (hasB) st_stream(out + o + p.obs, make_float2(yb.x * scale, yb.y * scale));
+        }
+}
+
+// plain twiddle tables: tw1[(k-1)*NT + t] = w_L^(t k), tw2[(k-1)*NT/16 + m] = w_L^(16 m k), contiguous
+template <int L>
+int get_plain_plan(Handle* h, const float2** tw1, const float2** tw2) {
+    using G = Geo<L>;
+    TwKey key{L, PB_C64, 12};
+    const float2* base = nullptr;
+    auto it = h->tables.find(key);
+    if (it != h->tables.end()) base = reinterpret_cast<const float2*>(it->second);
+    else {
+        std::vector<std::complex<double>> tab(15 * G::NT + 15 * (G::NT / 16));
+        auto w = [&](long long num, long long den) {
+            num %= den;
+            const double a = -2.0 * 3.14159265358979323846 * (double)num / (double)den;
+            return std::complex<double>(cos(a), sin(a));
+        };
+        for (int k = 1; k < 16; ++k)
+            for (int t = 0; t < G::NT; ++t) tab[(k - 1) * G::NT + t] = w((long long)t * k, L);
+        for (int k = 1; k < 16; ++k)
+            for (int m = 0; m < G::NT / 16; ++m) tab[15 * G::NT + (k - 1) * (G::NT / 16) + m] = w(16LL * m * k, L);
+        const void* d = nullptr;
+        PB_TRY(upload_table(h, key, tab, &d));
+        base = reinterpret_cast<const float2*>(d);
+    }
+    *tw1 = base;
+    *tw2 = base + 15 * G::NT;
+    return PB_OK;
+}
+
+template <int L, bool INV, bool COLS>
+int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
+    using G = Geo<L>;
+    constexpr int TP = COLS ? (L >= 4096 ? 2 : 2) : 1;
+    const size_t smem = (size_t)TP * (G::SBUF + 2) * sizeof(float4);
+    static bool attr = false;
+    if (!attr) {
+        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // keep >= 64 KB of L1 for the twiddle tables (see launch_focus)
+        const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
+        const int ctas = std::max<int>(1, (int)((unified - l1_keep) / (smem + 1024)));
+        const int pct = (int)std::min<size_t>(100, ((size_t)ctas * (smem + 1024) * 100 + h->max_smem_optin - 1) / h->max_smem_optin);
+        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        attr = true;
+    }
+    const float2 *tw1 = nullptr, *tw2 = nullptr;
+    PB_TRY(get_plain_plan<L>(h, &tw1, &tw2));
+    const int lines_per_cta = 2 * TP;
+    const int grid = (p.nb + lines_per_cta - 1) / lines_per_cta;
+    axis_reg_kernel<L, INV, COLS, TP><<<grid, TP * G::NT, smem, st>>>(p, tw1, tw2);
+    PB_LAUNCH_CHECK(h);
+    return PB_OK;
+}
+
+template <int L>
+int dispatch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
+    const bool cols = p.batch_contiguous != 0;
+    if (p.dir < 0) return cols ? launch_axis_reg<L, false, true>(h, p, st) : launch_axis_reg<L, false, false>(h, p, st);
+    return cols ? launch_axis_reg<L, true, true>(h, p, st) : launch_axis_reg<L, true, false>(h, p, st);
+}
+
 }  // namespace
 
-int try_tuned_axis_pass(Handle*, const AxisPass&, cudaStream_t) { return PB_ERR_UNSUPPORTED; }
+int try_tuned_axis_pass(Handle* h, const AxisPass& p, cudaStream_t st) {
+    static const bool disabled = getenv("PB_DISABLE_TUNED") != nullptr || getenv("PB_DISABLE_TUNED_AXIS") != nullptr;
+    if (disabled) return PB_ERR_UNSUPPORTED;
+    if (p.dtype != PB_C64 || p.in_kind != PB_IN_COMPLEX || p.out_kind != PB_OUT_COMPLEX) return PB_ERR_UNSUPPORTED;
+    if (p.pre_e2 || p.post_e2 || p.post_mat) return PB_ERR_UNSUPPORTED;
+    if (p.Llog != p.L || (p.Llog_out != 0 && p.Llog_out != p.L)) return PB_ERR_UNSUPPORTED;
+    if (p.nb < 8) return PB_ERR_UNSUPPORTED;  // tiny batches: the generic kernel is as good
+    switch (p.L) {
+        case 1024: return dispatch_axis_reg<1024>(h, p, st);
+        case 2048: return dispatch_axis_reg<2048>(h, p, st);
+        case 4096: return dispatch_axis_reg<4096>(h, p, st);
+        default: return PB_ERR_UNSUPPORTED;
+    }
+}
 
 int try_tuned_fft2(Handle* h, int dtype, const void* in, int in_kind, const void* amp, int amp_kind, double kturns,
                    int ny, int nx, long long in_ld, int ky, int kx, int dir, double scale, int shift_in, int shift_out,

@@ -62,3 +62,16 @@ def mtf_ptf_otf_from_psf(psf, dx=None, return_more=False):
     mtf, ptf, otf, data, df = _normalized(psf, dx, 7)
     out = (RichData(mtf, df, None), RichData(ptf, df, None), RichData(otf, df, None))
     return out + (data,) if return_more else out
+
+
+def encircled_energy(psf, dx, radius, return_more=False):
+    """Baliga & Cohn encircled energy at `radius` [um] (scalar or iterable) from the MTF of the PSF
+    (prysm/otf.py:346-387): one reduction kernel per call covers all radii."""
+    import numbers
+    import numpy as np
+    mtf, data = mtf_from_psf(psf, dx, return_more=True)
+    scalar = isinstance(radius, numbers.Number)
+    radii = np.atleast_1d(np.asarray(radius, dtype=np.float64)) / 1e3
+    out = _ops.encircled_energy(mtf.data, mtf.dx, radii)
+    out = float(out[0]) if scalar else out
+    return (out, data) if return_more else out
