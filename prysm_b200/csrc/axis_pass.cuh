@@ -45,6 +45,9 @@ struct AxisPass {
     double weight = 1.0;
     // mapping hint: 1 when consecutive batches are adjacent in memory (column pass)
     int batch_contiguous = 0;
+    // tuned kernels only: forward transform, multiply by post_e/post_b, inverse transform, then crop/store
+    // (the column half of a free-space step in one kernel); the generic kernel never sees this flag
+    int roundtrip = 0;
 };
 
 // L must be a power of two here (Bluestein is composed one level up).

@@ -275,6 +275,24 @@ extern "C" int pb_angular_spectrum(pb_handle_t hh, int dtype, const void* in, in
     p.Llog = kx; p.n_in = nx; p.in_off = ceil_half(kx - nx);
     p.dir = -1; p.out = t0; p.obs = kx; p.oes = 1; p.n_out = kx;
     PB_TRY(axis_dft(h, p, st));
+    if (!tf && dtype == PB_C64) {  // separable TF: forward * TF * inverse along y in ONE tuned pass, if it is covered
+        AxisPass f;
+        f.dtype = dtype; f.in = t0; f.ibs = 1; f.ies = kx; f.nb = kx;
+        f.L = ky; f.Llog = ky; f.n_in = ny; f.in_off = ceil_half(ky - ny);
+        f.dir = -1; f.out = t1; f.obs = 1; f.oes = kx; f.n_out = oy; f.crop_off = ceil_half(ky - oy); f.batch_contiguous = 1;
+        f.post_e = ty; f.post_e_conj = conj_tf; f.post_b = tx; f.post_b_conj = conj_tf;
+        f.roundtrip = 1;
+        int frc = is_pow2(ky) ? try_tuned_axis_pass(h, f, st) : PB_ERR_UNSUPPORTED;
+        if (frc == PB_OK) {
+            AxisPass s2;  // rows inverse from t1 (oy, kx), keep the ox centred columns, 1/(ky*kx)
+            s2.dtype = dtype; s2.in = t1; s2.ibs = kx; s2.ies = 1; s2.nb = oy;
+            s2.Llog = kx; s2.n_in = kx; s2.dir = +1;
+            s2.out = out; s2.obs = ox; s2.oes = 1; s2.n_out = ox; s2.crop_off = ceil_half(kx - ox);
+            s2.scale = 1.0 / ((double)ky * (double)kx);
+            return axis_dft(h, s2, st);
+        }
+        if (frc != PB_ERR_UNSUPPORTED) return frc;
+    }
     AxisPass q;  // columns forward, times the transfer function -> t1 (ky, kx)
     q.dtype = dtype; q.in = t0; q.ibs = 1; q.ies = kx; q.nb = kx;
     q.Llog = ky; q.n_in = ny; q.in_off = ceil_half(ky - ny);

@@ -492,7 +492,7 @@ __device__ __forceinline__ float2 cmul_s(float2 a, float2 b, int conj) {
                 : make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-template <int L, bool INV, bool COLS, int TP>
+template <int L, bool INV, bool COLS, int TP, bool RT>
 __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16) axis_reg_kernel(const AxisPass p, const float2* __restrict__ tw1,
                                                                             const float2* __restrict__ tw2) {
     using G = Geo<L>;
@@ -516,8 +516,14 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16) axis_reg_kernel(cons
         float2 xa = make_float2(0.f, 0.f), xb = xa;
         if (li >= 0 && li < p.n_in) {
             const long long o = (long long)b0 * p.ibs + (long long)li * p.ies;
-            if (hasA) xa = ld_stream(in + o);
-            if (hasB) xb = ld_stream(in + o + p.ibs);
+            if (p.in_kind == PB_IN_REAL) {   // real field (the PSF going to transform_psf): imaginary part 0
+                const float* __restrict__ inr = reinterpret_cast<const float*>(p.in);
+                if (hasA) xa.x = __ldg(inr + o);
+                if (hasB) xb.x = __ldg(inr + o + p.ibs);
+            } else {
+                if (hasA) xa = ld_stream(in + o);
+                if (hasB) xb = ld_stream(in + o + p.ibs);
+            }
             if (pre_e) { const float2 w = pre_e[j - p.pre_off]; xa = cmul_s(xa, w, p.pre_e_conj); xb = cmul_s(xb, w, p.pre_e_conj); }
             if (pre_b) { xa = cmul_s(xa, pbA, p.pre_b_conj); xb = cmul_s(xb, pbB, p.pre_b_conj); }
         }
@@ -534,6 +540,44 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16) axis_reg_kernel(cons
     if (post_b) { if (hasA) qbA = post_b[b0]; if (hasB) qbB = post_b[b0 + 1]; }
     const float scale = (float)p.scale;
     float2* __restrict__ out = reinterpret_cast<float2*>(p.out);
+    if (RT) {
+        // Round trip (free-space propagation along this axis): the spectrum is multiplied by the transfer
+        // factors post_e[k] * post_b[line] and transformed straight back.  The forward pass leaves thread t
+        // with X[t + NT*(g + GI*kk)], which IS the inverse pass's stage-1 register layout (n = g + GI*kk):
+        // the data never leaves the registers between the two transforms.
+        P2 w[16];
+#pragma unroll
+        for (int g = 0; g < G::GI; ++g)
+#pragma unroll
+            for (int kk = 0; kk < G::R3; ++kk) {
+                const int k = t + g * NT + 256 * kk;
+                const P2 y = v[g * G::R3 + kk];
+                float2 ya = make_float2(y.re.x, y.im.x), yb = make_float2(y.re.y, y.im.y);
+                if (post_e) { const float2 m = post_e[k - p.post_off]; ya = cmul_s(ya, m, p.post_e_conj); yb = cmul_s(yb, m, p.post_e_conj); }
+                if (post_b) { ya = cmul_s(ya, qbA, p.post_b_conj); yb = cmul_s(yb, qbB, p.post_b_conj); }
+                w[g + G::GI * kk] = {make_float2(ya.x, yb.x), make_float2(ya.y, yb.y)};
+            }
+        __syncthreads();   // all last-stage reads of S are done before the inverse pass overwrites it
+        fft_two_stages<L, !INV, 2>(w, t, S, tw1, tw2, SyncCta(), SyncCta());
+        fft_last_stage_load<L, !INV>(w, t, S);
+#pragma unroll
+        for (int g = 0; g < G::GI; ++g) dftR<G::R3, !INV>(w + g * G::R3);
+#pragma unroll
+        for (int g = 0; g < G::GI; ++g)
+#pragma unroll
+            for (int kk = 0; kk < G::R3; ++kk) {
+                const int j = t + g * NT + 256 * kk;
+                int q = j - p.crop_off + p.rot_out;
+                if (q < 0) q += L;
+                if (q >= L) q -= L;
+                if (q >= p.n_out) continue;
+                const P2 y = w[g * G::R3 + kk];
+                const long long o = (long long)b0 * p.obs + (long long)q * p.oes;
+                if (hasA) st_stream(out + o, make_float2(y.re.x * scale, y.im.x * scale));
+                if (hasB) st_stream(out + o + p.obs, make_float2(y.re.y * scale, y.im.y * scale));
+            }
+        return;
+    }
 #pragma unroll
     for (int g = 0; g < G::GI; ++g)
 #pragma unroll
@@ -581,26 +625,26 @@ int get_plain_plan(Handle* h, const float2** tw1, const float2** tw2) {
     return PB_OK;
 }
 
-template <int L, bool INV, bool COLS>
+template <int L, bool INV, bool COLS, bool RT>
 int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     using G = Geo<L>;
     constexpr int TP = COLS ? (L >= 4096 ? 2 : 2) : 1;
     const size_t smem = (size_t)TP * (G::SBUF + 2) * sizeof(float4);
     static bool attr = false;
     if (!attr) {
-        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // keep >= 64 KB of L1 for the twiddle tables (see launch_focus)
         const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
         const int ctas = std::max<int>(1, (int)((unified - l1_keep) / (smem + 1024)));
         const int pct = (int)std::min<size_t>(100, ((size_t)ctas * (smem + 1024) * 100 + h->max_smem_optin - 1) / h->max_smem_optin);
-        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         attr = true;
     }
     const float2 *tw1 = nullptr, *tw2 = nullptr;
     PB_TRY(get_plain_plan<L>(h, &tw1, &tw2));
     const int lines_per_cta = 2 * TP;
     const int grid = (p.nb + lines_per_cta - 1) / lines_per_cta;
-    axis_reg_kernel<L, INV, COLS, TP><<<grid, TP * G::NT, smem, st>>>(p, tw1, tw2);
+    axis_reg_kernel<L, INV, COLS, TP, RT><<<grid, TP * G::NT, smem, st>>>(p, tw1, tw2);
     PB_LAUNCH_CHECK(h);
     return PB_OK;
 }
@@ -608,8 +652,12 @@ int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
 template <int L>
 int dispatch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     const bool cols = p.batch_contiguous != 0;
-    if (p.dir < 0) return cols ? launch_axis_reg<L, false, true>(h, p, st) : launch_axis_reg<L, false, false>(h, p, st);
-    return cols ? launch_axis_reg<L, true, true>(h, p, st) : launch_axis_reg<L, true, false>(h, p, st);
+    if (p.roundtrip) {
+        if (!cols) return PB_ERR_UNSUPPORTED;
+        return p.dir < 0 ? launch_axis_reg<L, false, true, true>(h, p, st) : launch_axis_reg<L, true, true, true>(h, p, st);
+    }
+    if (p.dir < 0) return cols ? launch_axis_reg<L, false, true, false>(h, p, st) : launch_axis_reg<L, false, false, false>(h, p, st);
+    return cols ? launch_axis_reg<L, true, true, false>(h, p, st) : launch_axis_reg<L, true, false, false>(h, p, st);
 }
 
 }  // namespace
@@ -617,7 +665,7 @@ int dispatch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
 int try_tuned_axis_pass(Handle* h, const AxisPass& p, cudaStream_t st) {
     static const bool disabled = getenv("PB_DISABLE_TUNED") != nullptr || getenv("PB_DISABLE_TUNED_AXIS") != nullptr;
     if (disabled) return PB_ERR_UNSUPPORTED;
-    if (p.dtype != PB_C64 || p.in_kind != PB_IN_COMPLEX || p.out_kind != PB_OUT_COMPLEX) return PB_ERR_UNSUPPORTED;
+    if (p.dtype != PB_C64 || p.in_kind == PB_IN_AMP_OPD || p.out_kind != PB_OUT_COMPLEX) return PB_ERR_UNSUPPORTED;
     if (p.pre_e2 || p.post_e2 || p.post_mat) return PB_ERR_UNSUPPORTED;
     if (p.Llog != p.L || (p.Llog_out != 0 && p.Llog_out != p.L)) return PB_ERR_UNSUPPORTED;
     if (p.nb < 8) return PB_ERR_UNSUPPORTED;  // tiny batches: the generic kernel is as good
