@@ -103,6 +103,15 @@ int pb_axis_dft(pb_handle_t h, int dtype, const void* in, int ny, int nx, long l
                 const void* post_e, int post_e_conj, const void* post_b, int post_b_conj,
                 int out_off, int n_out, void* out, long long out_ld, void* stream);
 
+/* ---- one Bluestein axis of the chirp-z transform, fused -----------------------------------
+ * For every line along `axis`:  u = line * pre_e (zero-extended to K);  c = IFFT_K( FFT_K(u) * H );
+ * out_line[q] = c[q + out_off] * post_e[q] * scale,  q in [0, n_out).   K must be a power of two.
+ * On the tuned path the data stays in registers between the two transforms (one kernel, one read and one
+ * write of the array).  Replaces the per-axis block of CZT.__call__ / adjoint, prysm/fttools.py:296-361. */
+int pb_czt_axis(pb_handle_t h, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int K,
+                const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj,
+                int out_off, int n_out, double scale, void* out, long long out_ld, void* stream);
+
 /* ---- angular spectrum ------------------------------------------------------------------
  * out(ky,kx) = ifft2( fft2( pad(in -> ky,kx) ) * TF ), TF = outer(ty, tx) when tf == NULL,
  * else the full (ky,kx) array tf; conj_tf applies conj(TF) (adjoint); the result is cropped to

@@ -153,6 +153,19 @@ def axis_dft(a, n, axis, dir=-1, scale=1.0, pre_e=None, pre_e_conj=False, pre_b=
     return out
 
 
+def czt_axis(a, K, axis, pre_e, H, post_e, out_off, n_out, scale=1.0, pre_conj=False, post_conj=False):
+    """pb_czt_axis: (a*pre_e) -> FFT_K -> *H -> IFFT_K -> [out_off:out_off+n_out] -> *post_e*scale along `axis`."""
+    a = ascomplex(a).contiguous()
+    ny, nx = a.shape
+    axis = axis % 2
+    oshape = (n_out, nx) if axis == 0 else (ny, n_out)
+    out = torch.empty(oshape, dtype=a.dtype, device=a.device)
+    h, st = _ctx(a)
+    h.check(lib.pb_czt_axis(h.ptr, _CODE[a.dtype], _p(a), ny, nx, nx, axis, int(K), _p(pre_e), int(pre_conj), _p(H),
+                            _p(post_e), int(post_conj), int(out_off), int(n_out), float(scale), _p(out), oshape[1], st))
+    return out
+
+
 def angular_spectrum(field, k, ty=None, tx=None, tf=None, conj_tf=False, crop=None):
     field = ascomplex(field).contiguous()
     ny, nx = field.shape

@@ -253,6 +253,43 @@ extern "C" int pb_axis_dft(pb_handle_t hh, int dtype, const void* in, int ny, in
     return axis_dft(h, p, st);
 }
 
+extern "C" int pb_czt_axis(pb_handle_t hh, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int K,
+                           const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj, int out_off,
+                           int n_out, double scale, void* out, long long out_ld, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h) return PB_ERR_INVALID;
+    if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
+    if (ny < 1 || nx < 1 || K < 1 || (axis != 0 && axis != 1) || !H) return fail(h, PB_ERR_INVALID, "bad czt arguments");
+    if (out_off < 0 || n_out < 1 || out_off + n_out > K) return fail(h, PB_ERR_INVALID, "output window outside the transform");
+    if (!is_pow2(K)) return fail(h, PB_ERR_INVALID, "the Bluestein length K must be a power of two");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nline = axis == 1 ? ny : nx, n_in = std::min(axis == 1 ? nx : ny, K);
+    AxisPass f;  // fused: (in * pre) -> FFT_K -> * H -> IFFT_K -> window -> * post
+    f.dtype = dtype; f.in = in; f.dir = -1; f.out = out; f.scale = scale / K;
+    f.L = K; f.Llog = K; f.n_in = n_in; f.n_out = n_out; f.crop_off = out_off; f.nb = nline;
+    f.pre_e = pre_e; f.pre_e_conj = pre_conj;
+    f.post_e = H;
+    f.post_e2 = post_e; f.post_e2_conj = post_conj;
+    if (axis == 1) { f.ibs = in_ld; f.ies = 1; f.obs = out_ld; f.oes = 1; f.batch_contiguous = 0; }
+    else { f.ibs = 1; f.ies = in_ld; f.obs = 1; f.oes = out_ld; f.batch_contiguous = 1; }
+    f.roundtrip = 1;
+    int rc = try_tuned_axis_pass(h, f, st);
+    if (rc != PB_ERR_UNSUPPORTED) return rc;
+    // two passes through a (lines x K) scratch
+    void* tmp = nullptr;
+    PB_TRY(ensure_scratch(h, 1, (size_t)nline * K * csize(dtype), &tmp));
+    AxisPass a = f;
+    a.roundtrip = 0; a.post_e2 = nullptr; a.out = tmp; a.n_out = K; a.crop_off = 0; a.scale = 1.0;
+    if (axis == 1) { a.obs = K; a.oes = 1; } else { a.obs = 1; a.oes = nline; }
+    PB_TRY(axis_dft(h, a, st));
+    AxisPass b;
+    b.dtype = dtype; b.in = tmp; b.dir = +1; b.out = out; b.scale = scale / K;
+    b.Llog = K; b.n_in = K; b.n_out = n_out; b.crop_off = out_off; b.nb = nline;
+    b.post_e = post_e; b.post_e_conj = post_conj; b.post_off = out_off;
+    b.ibs = a.obs; b.ies = a.oes; b.obs = f.obs; b.oes = f.oes; b.batch_contiguous = f.batch_contiguous;
+    return axis_dft(h, b, st);
+}
+
 extern "C" int pb_angular_spectrum(pb_handle_t hh, int dtype, const void* in, int ny, int nx, int ky, int kx,
                                    const void* ty, const void* tx, const void* tf, int conj_tf, void* out, int oy,
                                    int ox, void* stream) {

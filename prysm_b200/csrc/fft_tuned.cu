@@ -572,9 +572,14 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16) axis_reg_kernel(cons
                 if (q >= L) q -= L;
                 if (q >= p.n_out) continue;
                 const P2 y = w[g * G::R3 + kk];
+                float2 ya = make_float2(y.re.x, y.im.x), yb = make_float2(y.re.y, y.im.y);
+                if (p.post_e2) {  // final multiplier, indexed by the output sample (the CZT's a(m)*phase(m))
+                    const float2 m = reinterpret_cast<const float2*>(p.post_e2)[q];
+                    ya = cmul_s(ya, m, p.post_e2_conj); yb = cmul_s(yb, m, p.post_e2_conj);
+                }
                 const long long o = (long long)b0 * p.obs + (long long)q * p.oes;
-                if (hasA) st_stream(out + o, make_float2(y.re.x * scale, y.im.x * scale));
-                if (hasB) st_stream(out + o + p.obs, make_float2(y.re.y * scale, y.im.y * scale));
+                if (hasA) st_stream(out + o, make_float2(ya.x * scale, ya.y * scale));
+                if (hasB) st_stream(out + o + p.obs, make_float2(yb.x * scale, yb.y * scale));
             }
         return;
     }
@@ -653,8 +658,8 @@ template <int L>
 int dispatch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     const bool cols = p.batch_contiguous != 0;
     if (p.roundtrip) {
-        if (!cols) return PB_ERR_UNSUPPORTED;
-        return p.dir < 0 ? launch_axis_reg<L, false, true, true>(h, p, st) : launch_axis_reg<L, true, true, true>(h, p, st);
+        if (p.dir < 0) return cols ? launch_axis_reg<L, false, true, true>(h, p, st) : launch_axis_reg<L, false, false, true>(h, p, st);
+        return cols ? launch_axis_reg<L, true, true, true>(h, p, st) : launch_axis_reg<L, true, false, true>(h, p, st);
     }
     if (p.dir < 0) return cols ? launch_axis_reg<L, false, true, false>(h, p, st) : launch_axis_reg<L, false, false, false>(h, p, st);
     return cols ? launch_axis_reg<L, true, true, false>(h, p, st) : launch_axis_reg<L, true, false, false>(h, p, st);
@@ -666,7 +671,7 @@ int try_tuned_axis_pass(Handle* h, const AxisPass& p, cudaStream_t st) {
     static const bool disabled = getenv("PB_DISABLE_TUNED") != nullptr || getenv("PB_DISABLE_TUNED_AXIS") != nullptr;
     if (disabled) return PB_ERR_UNSUPPORTED;
     if (p.dtype != PB_C64 || p.in_kind == PB_IN_AMP_OPD || p.out_kind != PB_OUT_COMPLEX) return PB_ERR_UNSUPPORTED;
-    if (p.pre_e2 || p.post_e2 || p.post_mat) return PB_ERR_UNSUPPORTED;
+    if (p.pre_e2 || (p.post_e2 && !p.roundtrip) || p.post_mat) return PB_ERR_UNSUPPORTED;
     if (p.Llog != p.L || (p.Llog_out != 0 && p.Llog_out != p.L)) return PB_ERR_UNSUPPORTED;
     if (p.nb < 8) return PB_ERR_UNSUPPORTED;  // tiny batches: the generic kernel is as good
     switch (p.L) {

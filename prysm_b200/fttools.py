@@ -181,38 +181,34 @@ class CZT:
         if tuple(o.shape) != (self._Ny, self._Nx):
             raise ValueError(f'array of shape {tuple(o.shape)} does not match the executor')
         Kx, Ky = self._Kx, self._Ky
+        # per axis ONE fused call: chirp -> FFT_K -> kernel spectrum -> IFFT_K -> slice -> chirp*phase.
+        # (the row chirp by[y] of the reference's `out *= brow` commutes with the x pass: it is the y pass's pre_e)
+        def along_x(o, scale):
+            return _ops.czt_axis(o, Kx, 1, self._bx, self._Hx, self._postx, self._Nx - 1, self._Mx, scale)
+
+        def along_y(o, scale):
+            return _ops.czt_axis(o, Ky, 0, self._by, self._Hy, self._posty, self._Ny - 1, self._My, scale)
+
         if self._x_first:
-            o = _ops.axis_dft(o, Kx, 1, -1, pre_e=self._bx, pre_b=self._by, post_e=self._Hx)
-            o = _ops.axis_dft(o, Kx, 1, +1, scale=1.0 / Kx, out_off=self._Nx - 1, n_out=self._Mx, post_e=self._postx)
-            o = _ops.axis_dft(o, Ky, 0, -1, post_e=self._Hy)
-            o = _ops.axis_dft(o, Ky, 0, +1, scale=self.norm / Ky, out_off=self._Ny - 1, n_out=self._My, post_e=self._posty)
-        else:
-            o = _ops.axis_dft(o, Ky, 0, -1, pre_e=self._by, pre_b=self._bx, post_e=self._Hy)
-            o = _ops.axis_dft(o, Ky, 0, +1, scale=1.0 / Ky, out_off=self._Ny - 1, n_out=self._My, post_e=self._posty)
-            o = _ops.axis_dft(o, Kx, 1, -1, post_e=self._Hx)
-            o = _ops.axis_dft(o, Kx, 1, +1, scale=self.norm / Kx, out_off=self._Nx - 1, n_out=self._Mx, post_e=self._postx)
-        return o
+            return along_y(along_x(o, 1.0), self.norm)
+        return along_x(along_y(o, 1.0), self.norm)
 
     def adjoint(self, grad):
         o = _prep(grad, self._bx.dtype)
         if tuple(o.shape) != (self._My, self._Mx):
             raise ValueError(f'array of shape {tuple(o.shape)} does not match the executor')
         Kx, Ky = self._Kx, self._Ky
+
+        # conj(post) -> FFT_K -> conj(H) with the embedding offset folded in -> IFFT_K -> [:N] -> conj(chirp)
+        def back_x(o, scale):
+            return _ops.czt_axis(o, Kx, 1, self._postx, self._Hadjx, self._bx, 0, self._Nx, scale, pre_conj=True, post_conj=True)
+
+        def back_y(o, scale):
+            return _ops.czt_axis(o, Ky, 0, self._posty, self._Hadjy, self._by, 0, self._Ny, scale, pre_conj=True, post_conj=True)
+
         if self._x_first:  # undo y then x
-            o = _ops.axis_dft(o, Ky, 0, -1, pre_e=self._posty, pre_e_conj=True, pre_b=self._postx, pre_b_conj=True,
-                              post_e=self._Hadjy)
-            o = _ops.axis_dft(o, Ky, 0, +1, scale=1.0 / Ky, n_out=self._Ny)
-            o = _ops.axis_dft(o, Kx, 1, -1, post_e=self._Hadjx)
-            o = _ops.axis_dft(o, Kx, 1, +1, scale=self.norm / Kx, n_out=self._Nx, post_e=self._bx, post_e_conj=True,
-                              post_b=self._by, post_b_conj=True)
-        else:
-            o = _ops.axis_dft(o, Kx, 1, -1, pre_e=self._postx, pre_e_conj=True, pre_b=self._posty, pre_b_conj=True,
-                              post_e=self._Hadjx)
-            o = _ops.axis_dft(o, Kx, 1, +1, scale=1.0 / Kx, n_out=self._Nx)
-            o = _ops.axis_dft(o, Ky, 0, -1, post_e=self._Hadjy)
-            o = _ops.axis_dft(o, Ky, 0, +1, scale=self.norm / Ky, n_out=self._Ny, post_e=self._by, post_e_conj=True,
-                              post_b=self._bx, post_b_conj=True)
-        return o
+            return back_x(back_y(o, 1.0), self.norm)
+        return back_y(back_x(o, 1.0), self.norm)
 
     def nbytes(self):
         return sum(v.numel() * v.element_size() for v in (self._bx, self._Hx, self._postx, self._Hadjx,
