@@ -112,6 +112,12 @@ int pb_czt_axis(pb_handle_t h, int dtype, const void* in, int ny, int nx, long l
                 const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj,
                 int out_off, int n_out, double scale, void* out, long long out_ld, void* stream);
 
+/* The Bluestein pieces of one CZT axis built on the device from scalars (no host maths, no uploads):
+ * b (N), post = a*phase (M), H = FFT_K(h) (K), Hadj (K) as consumed by pb_czt_axis.  alpha = dx*dfx,
+ * shift = f[M/2]/df, xc = x[N/2], f0 = f[0], df the frequency step.  prysm/fttools.py:257-291, 372-389 */
+int pb_czt_plan(pb_handle_t h, int dtype, int N, int M, int K, double shift, double alpha, int sign,
+                double xc, double f0, double df, void* b, void* post, void* H, void* Hadj, void* stream);
+
 /* ---- angular spectrum ------------------------------------------------------------------
  * out(ky,kx) = ifft2( fft2( pad(in -> ky,kx) ) * TF ), TF = outer(ty, tx) when tf == NULL,
  * else the full (ky,kx) array tf; conj_tf applies conj(TF) (adjoint); the result is cropped to

@@ -153,6 +153,18 @@ def axis_dft(a, n, axis, dir=-1, scale=1.0, pre_e=None, pre_e_conj=False, pre_b=
     return out
 
 
+def czt_plan(N, M, K, shift, alpha, sign, xc, f0, df, cdtype, dev):
+    """pb_czt_plan: (b, post, H, Hadj) for one axis, built on the device."""
+    b = torch.empty(N, dtype=cdtype, device=dev)
+    post = torch.empty(M, dtype=cdtype, device=dev)
+    H = torch.empty(K, dtype=cdtype, device=dev)
+    Hadj = torch.empty(K, dtype=cdtype, device=dev)
+    h, st = _ctx(b)
+    h.check(lib.pb_czt_plan(h.ptr, _CODE[cdtype], int(N), int(M), int(K), float(shift), float(alpha), int(sign), float(xc),
+                            float(f0), float(df), _p(b), _p(post), _p(H), _p(Hadj), st))
+    return b, post, H, Hadj
+
+
 def czt_axis(a, K, axis, pre_e, H, post_e, out_off, n_out, scale=1.0, pre_conj=False, post_conj=False):
     """pb_czt_axis: (a*pre_e) -> FFT_K -> *H -> IFFT_K -> [out_off:out_off+n_out] -> *post_e*scale along `axis`."""
     a = ascomplex(a).contiguous()

@@ -153,6 +153,45 @@ __global__ void encircled_energy_kernel(const R* __restrict__ mtf, int ny, int n
     }
 }
 
+// Bluestein pieces of one CZT axis built on the device from scalars (prysm/fttools.py:372-389, 277-281):
+//   b[n]    = exp(sign*i*pi*alpha*n^2),            n = -(N/2) .. ;      N entries
+//   post[m] = exp(sign*i*pi*alpha*(m+shift)^2) * exp(sign*2*pi*i*xc*f[m]),  f[m] = f0 + m*df;   M entries
+//   h[d]    = exp(-sign*i*pi*alpha*(d+shift)^2),   d = m0-n_last .. m_last-n0, zero-extended to K entries
+// all phases in fp64 turns, reduced before the sincos.
+template <typename R>
+__global__ void czt_plan_kernel(int N, int M, int K, double shift, double alpha, int sign, double xc, double f0, double df,
+                                cplx<R>* __restrict__ b, cplx<R>* __restrict__ post, cplx<R>* __restrict__ hk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double half = 0.5 * sign * alpha;
+    if (i < N) {
+        const double n = (double)(i - N / 2);
+        b[i] = expi_turns(half * n * n, R(0));
+    }
+    if (i < M) {
+        const double q = (double)(i - M / 2) + shift;
+        post[i] = expi_turns(half * q * q + sign * xc * (f0 + i * df), R(0));
+    }
+    if (i < K) {
+        const int nd = N + M - 1;
+        cplx<R> v = mk<R>(R(0), R(0));
+        if (i < nd) {
+            const double d = (double)(i + (-(M / 2)) - (-(N / 2) + N - 1)) + shift;   // m0 - n_last + i + shift
+            v = expi_turns(-half * d * d, R(0));
+        }
+        hk[i] = v;
+    }
+}
+
+// Hadj[k] = conj(H[k]) * exp(-2*pi*i*(N-1)*k/K): the adjoint's embedding at offset N-1 as a spectral phase
+template <typename R>
+__global__ void czt_hadj_kernel(int N, int K, const cplx<R>* __restrict__ H, cplx<R>* __restrict__ Hadj) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const long long r = ((long long)(N - 1) * k) % K;
+    const cplx<R> ph = expi_turns(-(double)r / (double)K, R(0));
+    Hadj[k] = cmul(cconj(H[k]), ph);
+}
+
 // exp(-i*pi*wvl_mm*z*k^2), k = fftfreq(n, dx).  The phase is formed in fp64 for both dtypes
 // (the reference rounds k to float32 first when precision=32, costing it ~1e-4 rad at C5 sizes).
 template <typename R>
@@ -306,6 +345,24 @@ extern "C" int pb_encircled_energy(pb_handle_t hh, int dtype, const void* mtf, i
     PB_LAUNCH_CHECK(h);
     PB_CUDA(h, cudaMemcpyAsync(out_host, dout, nr * sizeof(double), cudaMemcpyDeviceToHost, st));
     PB_CUDA(h, cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+extern "C" int pb_czt_plan(pb_handle_t hh, int dtype, int N, int M, int K, double shift, double alpha, int sign, double xc,
+                           double f0, double df, void* b, void* post, void* H, void* Hadj, void* stream) {
+    PB_HANDLE(hh);
+    if (N < 1 || M < 1 || K < N + M - 1 || (sign != 1 && sign != -1) || !b || !post || !H || !Hadj)
+        return fail(h, PB_ERR_INVALID, "bad czt plan arguments");
+    const int n = std::max(K, std::max(N, M));
+    void* hk = nullptr;
+    PB_TRY(ensure_scratch(h, 2, (size_t)K * csize(dtype), &hk));
+    if (dtype == PB_C64) czt_plan_kernel<float><<<(n + 255) / 256, 256, 0, st>>>(N, M, K, shift, alpha, sign, xc, f0, df, (float2*)b, (float2*)post, (float2*)hk);
+    else czt_plan_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(N, M, K, shift, alpha, sign, xc, f0, df, (double2*)b, (double2*)post, (double2*)hk);
+    PB_LAUNCH_CHECK(h);
+    PB_TRY(pb_fft1(hh, dtype, hk, 1, K, K, 1, K, -1, 1.0, H, K, stream));   // H = FFT_K(h)
+    if (dtype == PB_C64) czt_hadj_kernel<float><<<(K + 255) / 256, 256, 0, st>>>(N, K, (const float2*)H, (float2*)Hadj);
+    else czt_hadj_kernel<double><<<(K + 255) / 256, 256, 0, st>>>(N, K, (const double2*)H, (double2*)Hadj);
+    PB_LAUNCH_CHECK(h);
     return PB_OK;
 }
 

@@ -165,15 +165,18 @@ class CZT:
         Nx, Mx, Ny, My = len(x), len(fx), len(y), len(fy)
         dx, dfx = float(x[1] - x[0]), float(fx[1] - fx[0])
         dy, dfy = float(y[1] - y[0]), float(fy[1] - fy[0])
-        ax = _CztAxis(Nx, Mx, float(fx[Mx // 2]) / dfx, dx * dfx, sign, float(x[Nx // 2]), fx)
-        ay = _CztAxis(Ny, My, float(fy[My // 2]) / dfy, dy * dfy, sign, float(y[Ny // 2]), fy)
         cd = config.complex_dtype
-        up = lambda v: _ops.asdevice(v.astype(config.precision_complex), cd)  # noqa: E731
-        self._bx, self._Hx, self._postx, self._Hadjx = up(ax.b), up(ax.H), up(ax.post), up(ax.Hadj)
-        self._by, self._Hy, self._posty, self._Hadjy = up(ay.b), up(ay.H), up(ay.post), up(ay.Hadj)
-        self._Nx, self._Ny, self._Mx, self._My, self._Kx, self._Ky = Nx, Ny, Mx, My, ax.K, ay.K
-        x_first_cost = Ny * ax.K * math.log2(ax.K) + Mx * ay.K * math.log2(ay.K)
-        y_first_cost = Nx * ay.K * math.log2(ay.K) + My * ax.K * math.log2(ax.K)
+        dev = _ops.device()
+        Kx, Ky = next_fast_len(Nx + Mx - 1), next_fast_len(Ny + My - 1)
+        # the chirps, phase ramps and kernel spectra are built on the device from ten scalars per axis
+        # (fp64 phases): constructing an executor per wavelength costs no host maths and no uploads
+        self._bx, self._postx, self._Hx, self._Hadjx = _ops.czt_plan(
+            Nx, Mx, Kx, float(fx[Mx // 2]) / dfx, dx * dfx, sign, float(x[Nx // 2]), float(fx[0]), dfx, cd, dev)
+        self._by, self._posty, self._Hy, self._Hadjy = _ops.czt_plan(
+            Ny, My, Ky, float(fy[My // 2]) / dfy, dy * dfy, sign, float(y[Ny // 2]), float(fy[0]), dfy, cd, dev)
+        self._Nx, self._Ny, self._Mx, self._My, self._Kx, self._Ky = Nx, Ny, Mx, My, Kx, Ky
+        x_first_cost = Ny * Kx * math.log2(Kx) + Mx * Ky * math.log2(Ky)
+        y_first_cost = Nx * Ky * math.log2(Ky) + My * Kx * math.log2(Kx)
         self._x_first = x_first_cost <= y_first_cost
 
     def __call__(self, ary):
