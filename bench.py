@@ -313,7 +313,10 @@ def run_b200(args):
                        'propagations_per_step': BATCH, 'parallelism': f'replicas x{world}',
                        'l2_policy': f'{BATCH} distinct 32 MiB inputs + {OUT_RING} x 128 MiB output ring per step (>> 126 MB L2)'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src,
+                         # dram__bytes_read + dram__bytes_write of the two kernels of one propagation from the
+                         # committed `ncu --set full` captures (profiles/r01_ncu_full_summary.txt; cold cache, so the
+                         # 64 MiB intermediate is re-read from DRAM there; back to back it is served from L2)
+                         'traffic': 33631232 + 19407616 + 67170304 + 75995904, 'peak_source': peak_src,
                          'algorithmic_bytes_per_propagation': ALG_BYTES,
                          'kernel': 'fused focus pipeline (all passes of one propagation), per GPU',
                          'us_per_propagation': t_prop * 1e6},
