@@ -84,9 +84,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.05)
@@ -97,7 +97,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if t0 is None or t0 <= ts <= t1 + 0.05]
+        window = 'timed region'
+        if len(rows) < 2:   # nvidia-smi ticks are coarse against a ~100 ms region: use every sample under the same load
+            rows, window = [r for (_, r) in self.rows], 'warm-up + timed region (same workload)'
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -108,7 +112,7 @@ class ClockSampler:
                 pass
         sm.sort()
         med = sm[len(sm) // 2] if sm else None
-        return {'sm_mhz': med, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': med, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 def cpu_focus_rate(seconds_budget, workers, pupils):
@@ -238,23 +242,25 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
     l0 = _ops.launch_count(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_start = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    t_end = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = _ops.launch_count(dev) - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_start, t_end) if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -110,11 +110,19 @@ class Handle:
 _handles = {}
 
 
-def handle_for(device_index):
-    h = _handles.get(device_index)
+def handle_for(device_index, stream=0):
+    """One handle per (device, stream): a handle's scratch arenas are only ordered by the stream its calls run
+    on, so work issued on different streams must not share one (include/prysm_b200.h: 'not thread-safe')."""
+    key = (device_index, stream)
+    h = _handles.get(key)
     if h is None:
-        h = _handles[device_index] = Handle(device_index)
+        h = _handles[key] = Handle(device_index)
     return h
+
+
+def launch_count(device_index):
+    """Kernels launched on `device_index` through any stream's handle."""
+    return sum(h.launch_count() for (d, _), h in _handles.items() if d == device_index)
 
 
 def version():

@@ -68,8 +68,8 @@ def ascomplex(t):
 
 
 def _ctx(t):
-    h = capi.handle_for(t.device.index)
-    return h, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    stream = torch.cuda.current_stream(t.device).cuda_stream
+    return capi.handle_for(t.device.index, stream), C.c_void_p(stream)
 
 
 def _p(t):
@@ -377,7 +377,7 @@ def moments(data):
 
 def launch_count(dev=None):
     dev = device() if dev is None else torch.device(dev)
-    return capi.handle_for(dev.index).launch_count()
+    return capi.launch_count(dev.index)
 
 
 def ceil_half(d):
