@@ -120,6 +120,86 @@ for prec, rdt, cdt, eps in ((64, np.float64, np.complex128, 1e-13), (32, np.floa
     check(tag + 'centroid spatial', O.centroid(p.astype(np.float64), 1.5), psf.centroid(p.astype(np.float64), 1.5), 1e-12)
     check(tag + 'centroid pixels', O.centroid(p.astype(np.float64), unit='pixels'), psf.centroid(p.astype(np.float64), unit='pixels'), 1e-12)
 
+    # ---- adjoint twins of the elementwise steps and the otf reductions
+    from prysm.polynomials import sum_of_2d_modes_adjoint
+    a = rng.random((9, 12)).astype(rdt)
+    ph = (rng.standard_normal((9, 12)) * 40).astype(rdt)
+    a[2, 3] = 0
+    wf = Wavefront.from_amp_and_phase(a, ph, 0.55, 0.1)
+    bar = Wavefront(crand(rng, (9, 12), cdt), 0.55, 0.1)
+    ibar = rng.random((9, 12)).astype(rdt)
+    check(tag + 'intensity_adjoint', O.intensity_adjoint(wf.data, ibar), wf.intensity_adjoint(ibar).data, eps)
+    check(tag + 'from_amp_and_phase_adjoint_phase', O.from_amp_and_phase_adjoint_phase(wf.data, bar.data, 0.55),
+          wf.from_amp_and_phase_adjoint_phase(bar), eps)
+    check(tag + 'from_amp_and_phase_adjoint_amp', O.from_amp_and_phase_adjoint_amp(wf.data, bar.data, 0.55),
+          wf.from_amp_and_phase_adjoint_amp(bar), eps)
+    check(tag + 'from_amp_and_phase_adjoint_amp(phase)', O.from_amp_and_phase_adjoint_amp(wf.data, bar.data, 0.55, ph),
+          wf.from_amp_and_phase_adjoint_amp(bar, phase=ph), eps)
+    xg, yg = make_xy_grid((9, 12), dx=0.1)
+    xg, yg = xg.astype(rdt), yg.astype(rdt)
+    check(tag + 'thin_lens_adjoint', O.thin_lens_adjoint(250.0, 0.55, xg, yg, bar.data),
+          Wavefront.thin_lens_adjoint(250.0, 0.55, xg, yg, bar), 1e-5 if prec == 32 else 1e-12)
+    pp = rng.random((10, 13)).astype(rdt)
+    D = otf.transform_psf(pp, 1.5)[0]
+    rb = rng.standard_normal((10, 13)).astype(rdt)
+    cb = crand(rng, (10, 13), cdt)
+    check(tag + 'mtf_from_psf_adjoint', O.mtf_from_psf_adjoint(rb, D), otf.mtf_from_psf_adjoint(rb, data=D), eps)
+    check(tag + 'ptf_from_psf_adjoint', O.ptf_from_psf_adjoint(rb, D), otf.ptf_from_psf_adjoint(rb, data=D), eps)
+    check(tag + 'otf_from_psf_adjoint', O.otf_from_psf_adjoint(cb, D), otf.otf_from_psf_adjoint(cb, data=D), eps)
+    check(tag + 'encircled_energy_adjoint', O.encircled_energy_adjoint([0.3, -1.2], D, 1.5, [2.0, 7.5]),
+          otf.encircled_energy_adjoint([0.3, -1.2], dx=1.5, radius=[2.0, 7.5], data=D), 1e-5 if prec == 32 else 1e-12)
+    check(tag + 'sum_of_2d_modes_adjoint', O.sum_of_2d_modes_adjoint(modes, pp[:8, :9]), sum_of_2d_modes_adjoint(modes, pp[:8, :9]), eps)
+    # ---- coronagraph compositions (MDFT / CZT executors)
+    w = crand(rng, (14, 12), cdt)
+    g = crand(rng, (14, 12), cdt)
+    lyot_r = rng.random((14, 12)).astype(rdt)
+    lyot_c = crand(rng, (14, 12), cdt)
+    for kind in ('mdft', 'czt'):
+        ex_r = propagation.prepare_executor(0.25, (14, 12), 0.8, (10, 16), 0.55, 20.0, kind=kind)
+        ex_o = O.prepare_executor(0.25, (14, 12), 0.8, (10, 16), 0.55, 20.0, kind=kind, rdtype=rdt)
+        for fname, fpm in (('real', rng.random((10, 16)).astype(rdt)), ('cplx', crand(rng, (10, 16), cdt))):
+            t2 = tag + f'{kind} fpm={fname} '
+            got = O.to_fpm_and_back(w, fpm, ex_o, True)
+            ref = propagation.to_fpm_and_back(w, fpm, ex_r, return_more=True)
+            for nm, u, v in zip(('next', 'at_fpm', 'after_fpm'), got, ref):
+                check(t2 + 'to_fpm_and_back ' + nm, u, v, eps)
+            got = O.to_fpm_and_back_adjoint(g, fpm, ex_o, True, ref[1])
+            refa = propagation.to_fpm_and_back_adjoint(g, fpm, ex_r, return_more=True, return_fpm_grad=True, field_at_fpm=ref[1])
+            for nm, u, v in zip(('Eabar', 'Ebbar', 'inter', 'fpm_bar'), got, refa):
+                check(t2 + 'to_fpm_and_back_adjoint ' + nm, u, v, eps)
+            for lname, lyot in (('none', None), ('real', lyot_r), ('cplx', lyot_c)):
+                got = O.babinet(w, lyot, fpm, ex_o, True)
+                refb = propagation.babinet(w, lyot, fpm, ex_r, return_more=True)
+                for nm, u, v in zip(('after_lyot', 'at_fpm', 'after_fpm', 'at_lyot'), got, refb):
+                    check(t2 + f'babinet lyot={lname} ' + nm, u, v, eps)
+                got = O.babinet_adjoint(g, lyot, fpm, ex_o, refb[1], refb[3])
+                refg = propagation.babinet_adjoint(g, lyot, fpm, ex_r, field_at_fpm=refb[1], field_at_lyot=refb[3],
+                                                   return_fpm_grad=True, return_lyot_grad=True)
+                for nm, u, v in zip(('abar', 'fpm_bar', 'lyot_bar'), got, refg):
+                    check(t2 + f'babinet_adjoint lyot={lname} ' + nm, u, v, eps)
+        # multi-resolution stack, vortex mask
+        mr = propagation.prepare_multiresolution(0.1, (14, 12), 2.0, (12, 18), 0.55, 10.0, num_levels=3, fine_samples=10, kind=kind)
+        mo = O.prepare_multiresolution(0.1, (14, 12), 2.0, (12, 18), 0.55, 10.0, num_levels=3, fine_samples=10, kind=kind, rdtype=rdt)
+        for k in range(3):
+            check(tag + f'{kind} multires window[{k}]', mo.windows[k], mr.windows[k], eps)
+            check(tag + f'{kind} multires xf[{k}]', mo.xf[k], mr.xf[k], eps)
+            check(tag + f'{kind} multires yf[{k}]', mo.yf[k], mr.yf[k], eps)
+        vo, vr = O.vortex_phase_mask(2), propagation.vortex_phase_mask(2)
+        check(tag + 'vortex mask', vo(mo.xf[1], mo.yf[1]), vr(mr.xf[1], mr.yf[1]), eps)
+        got = O.to_fpm_and_back_multiresolution(w, vo, mo, True)
+        ref = propagation.to_fpm_and_back_multiresolution(w, vr, mr, return_more=True)
+        check(tag + f'{kind} multires forward', got[0], ref[0], eps)
+        for k in range(3):
+            check(tag + f'{kind} multires at_fpm[{k}]', got[1][k], ref[1][k], eps)
+            check(tag + f'{kind} multires after_fpm[{k}]', got[2][k], ref[2][k], eps)
+        got = O.to_fpm_and_back_multiresolution_adjoint(g, vo, mo, ref[1])
+        refa = propagation.to_fpm_and_back_multiresolution_adjoint(g, vr, mr, return_more=True, return_fpm_grad=True, field_at_fpm=ref[1])
+        check(tag + f'{kind} multires adjoint', got[0], refa[0], eps)
+        for k in range(3):
+            check(tag + f'{kind} multires Ebbar[{k}]', got[1][k], refa[1][k], eps)
+            check(tag + f'{kind} multires inter[{k}]', got[2][k], refa[2][k], eps)
+            check(tag + f'{kind} multires fpm_bar[{k}]', got[3][k], refa[3][k], eps)
+
 # pupil builder (fp64 maths, cast at the end)
 for j in range(1, 60):
     assert O.noll_to_nm(j) == noll_to_nm(j), j

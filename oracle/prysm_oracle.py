@@ -534,6 +534,258 @@ def centroid(data, dx=None, unit='spatial'):
 
 
 # --------------------------------------------------------------------------------------
+# adjoint twins of the elementwise steps and of the otf reductions
+# (prysm/propagation/_kernels.py:30-38, wavefront.py:172-298, otf.py:205-316, 417-471)
+# --------------------------------------------------------------------------------------
+
+
+def adjoint_multiply(grad, factor, real=False):
+    """Adjoint w.r.t. x of y = x*factor: grad*conj(factor).  prysm/propagation/_kernels.py:30-38."""
+    factor = np.asarray(factor)
+    out = grad * (np.conj(factor) if np.iscomplexobj(factor) else factor)
+    return np.real(out) if real else out
+
+
+def intensity_adjoint(field, intensity_bar):
+    """2 * Ibar * E.  prysm/propagation/wavefront.py:282-298."""
+    return 2 * intensity_bar * field
+
+
+def from_amp_and_phase_adjoint_phase(field, field_bar, wavelength):
+    """prefix * imag(gbar * conj(g)) with the COMPLEX prefix i*2pi/(1e3*wvl) of the forward step
+    (so the reference returns a purely imaginary array).  prysm/propagation/wavefront.py:172-188."""
+    return phase_prefix(wavelength) * np.imag(field_bar * np.conj(field))
+
+
+def from_amp_and_phase_adjoint_amp(field, field_bar, wavelength, phase=None):
+    """real(gbar * conj(S)), S the unit phasor -- rebuilt from `phase`, else P/|P| (0 where P = 0).
+    prysm/propagation/wavefront.py:190-225."""
+    if phase is not None:
+        S = np.exp(phase_prefix(wavelength) * phase)
+        return np.real(field_bar * np.conj(S))
+    mod = np.abs(field)
+    ok = mod > 0
+    g = np.real(field_bar * np.conj(field))
+    return np.where(ok, g / np.where(ok, mod, 1), 0)
+
+
+def thin_lens_adjoint(f, wavelength, x, y, lens_bar):
+    """d/df of the thin-lens screen folded with its gradient: pi/(w f^2) * sum(r^2 imag(Lbar conj(L))).
+    prysm/propagation/wavefront.py:244-280."""
+    L = thin_lens(f, wavelength, x, y)
+    w = wavelength / 1e3
+    return np.pi / (w * f * f) * np.sum((x * x + y * y) * np.imag(lens_bar * np.conj(L)))
+
+
+def transform_psf_adjoint(data_bar):
+    """fftshift(ifft2(ifftshift(g), norm='forward')).  prysm/otf.py:36-59."""
+    return sfft.fftshift(sfft.ifft2(sfft.ifftshift(data_bar), norm='forward'))
+
+
+def _centre(shape):
+    return tuple(int(np.floor(s / 2)) for s in shape)
+
+
+def mtf_from_psf_adjoint(mtf_bar, data):
+    """Through |.| and the division by the centre magnitude.  prysm/otf.py:205-242."""
+    cy, cx = _centre(data.shape)
+    mag = np.abs(data)
+    a = mag[cy, cx]
+    bar = mtf_bar * data / mag / a
+    bar[cy, cx] -= np.sum(mtf_bar * mag) * data[cy, cx] / a ** 3
+    return transform_psf_adjoint(bar).real
+
+
+def ptf_from_psf_adjoint(ptf_bar, data):
+    """Through angle(.) referenced to the centre phase.  prysm/otf.py:245-279."""
+    cy, cx = _centre(data.shape)
+    msq = data.real * data.real + data.imag * data.imag
+    bar = ptf_bar * 1j * data / msq
+    bar[cy, cx] -= np.sum(ptf_bar) * 1j * data[cy, cx] / msq[cy, cx]
+    return transform_psf_adjoint(bar).real
+
+
+def otf_from_psf_adjoint(otf_bar, data):
+    """Through the division by the centre sample.  prysm/otf.py:282-316."""
+    cy, cx = _centre(data.shape)
+    cc = np.conj(data[cy, cx])
+    bar = otf_bar / cc
+    bar[cy, cx] -= np.sum(np.conj(data) * otf_bar) / cc ** 2
+    return transform_psf_adjoint(bar).real
+
+
+def encircled_energy_adjoint(ee_bar, data, dx, radius):
+    """EE is linear in the MTF: fold the per-radius gradients into one MTF-plane gradient, then
+    mtf_from_psf_adjoint.  prysm/otf.py:417-471 (geometry: otf.py:319-343)."""
+    from scipy.special import j1
+    df = 1000 / (data.shape[0] * dx)
+    fy = fftrange(data.shape[0]) * df
+    fx = fftrange(data.shape[1]) * df
+    nu = np.hypot(*np.meshgrid(fx, fy))
+    nu[nu == 0] = 1e-16
+    radii = np.atleast_1d(np.asarray(radius, dtype=np.float64))
+    bars = np.atleast_1d(np.asarray(ee_bar, dtype=np.float64))
+    mtf_bar = 0.0
+    for rb, r in zip(bars, radii):
+        ri = r / 1e3
+        mtf_bar = mtf_bar + rb * ri * (j1(2 * np.pi * ri * nu) / nu) * df * df
+    return mtf_from_psf_adjoint(mtf_bar, data)
+
+
+def sum_of_2d_modes_adjoint(modes, databar):
+    """tensordot over the two trailing axes.  prysm/polynomials/fitting.py:40-57."""
+    return np.tensordot(np.asarray(modes), databar)
+
+
+# --------------------------------------------------------------------------------------
+# Lyot-family coronagraph compositions  (prysm/propagation/coronagraph.py, dft.py:155-294)
+# --------------------------------------------------------------------------------------
+
+
+def focus_dft_adjoint(g, ex):
+    """prysm/propagation/dft.py:316-332."""
+    return ex.adjoint(g)
+
+
+def unfocus_dft_adjoint(g, ex):
+    """prysm/propagation/dft.py:354-370."""
+    return ex(g)
+
+
+def to_fpm_and_back(w, fpm, ex, return_more=False):
+    """focus_dft -> * fpm -> unfocus_dft with one executor.  prysm/propagation/coronagraph.py:12-46."""
+    at_fpm = focus_dft(w, ex)
+    after_fpm = at_fpm * fpm
+    nxt = unfocus_dft(after_fpm, ex)
+    return (nxt, at_fpm, after_fpm) if return_more else nxt
+
+
+def to_fpm_and_back_adjoint(g, fpm, ex, return_fpm_grad=False, field_at_fpm=None):
+    """prysm/propagation/coronagraph.py:49-99.  Returns (Eabar, Ebbar, intermediate[, fpm_bar])."""
+    if return_fpm_grad and field_at_fpm is None:
+        raise ValueError('return_fpm_grad=True requires field_at_fpm from the forward propagation')
+    Ebbar = unfocus_dft_adjoint(g, ex)
+    inter = adjoint_multiply(Ebbar, fpm)
+    Eabar = focus_dft_adjoint(inter, ex)
+    if return_fpm_grad:
+        return Eabar, Ebbar, inter, adjoint_multiply(Ebbar, field_at_fpm, real=not np.iscomplexobj(fpm))
+    return Eabar, Ebbar, inter
+
+
+def babinet(w, lyot, fpm, ex, return_more=False):
+    """lyot * (w - to_fpm_and_back(w, 1 - fpm)).  prysm/propagation/coronagraph.py:301-353."""
+    field, at_fpm, after_fpm = to_fpm_and_back(w, 1 - fpm, ex, return_more=True)
+    at_lyot = w - field
+    after_lyot = at_lyot if lyot is None else lyot * at_lyot
+    return (after_lyot, at_fpm, after_fpm, at_lyot) if return_more else after_lyot
+
+
+def babinet_adjoint(g, lyot, fpm, ex, field_at_fpm=None, field_at_lyot=None):
+    """prysm/propagation/coronagraph.py:356-431.  Returns (abar, fpm_bar or None, lyot_bar or None); the
+    gradients are produced when the matching forward fields are given."""
+    lyot_complex = True if lyot is None else np.iscomplexobj(lyot)
+    B = 1 - fpm
+    cbar = g if lyot is None else adjoint_multiply(g, lyot)
+    fpm_bar = None
+    if field_at_fpm is not None:
+        abar, _, _, fpm_bar = to_fpm_and_back_adjoint(cbar, B, ex, True, field_at_fpm)
+    else:
+        abar = to_fpm_and_back_adjoint(cbar, B, ex)[0]
+    abar = cbar - abar
+    lyot_bar = None if field_at_lyot is None else adjoint_multiply(g, field_at_lyot, real=not lyot_complex)
+    return abar, fpm_bar, lyot_bar
+
+
+def vortex_phase_mask(charge):
+    """fpm(xf, yf) = exp(i*charge*atan2(yf, xf)).  prysm/propagation/coronagraph.py:102-132."""
+    import numbers
+    if not isinstance(charge, numbers.Integral):
+        raise TypeError(f'charge must be an integer, got {charge!r}; non-integer charge has a branch cut at theta=pi')
+
+    def fpm(xf, yf):
+        return np.exp((1j * charge) * np.arctan2(yf, xf))
+    return fpm
+
+
+def smootherstep(t):
+    """6t^5 - 15t^4 + 10t^3 on clip(t, 0, 1).  prysm/propagation/dft.py:155-158."""
+    t = np.clip(t, 0, 1)
+    return t * t * t * (t * (t * 6 - 15) + 10)
+
+
+def cumulative_window(r, a, b):
+    """1 inside a, 0 outside b, C2 in between.  prysm/propagation/dft.py:161-167."""
+    return 1 - smootherstep((r - a) / (b - a))
+
+
+class MultiResolutionExecutor:
+    """prysm/propagation/dft.py:170-209."""
+
+    def __init__(self, executors, windows, xf, yf):
+        self.executors, self.windows, self.xf, self.yf = executors, windows, xf, yf
+
+    def __len__(self):
+        return len(self.executors)
+
+
+def prepare_multiresolution(pupil_dx, pupil_samples, focal_dx, focal_samples, wavelength, efl, num_levels,
+                            scaling=4.0, fine_samples=None, window=(0.2, 0.7), kind='mdft', rdtype=np.float64):
+    """Level k: spacing focal_dx/scaling^k, half-sample focal shift, window = taper(own half-width) -
+    taper(next level's half-width); the windows telescope to one.  prysm/propagation/dft.py:212-294."""
+    if fine_samples is None:
+        fine_samples = focal_samples
+    inner, outer = window
+    exs, xfs, yfs, radii, halves = [], [], [], [], []
+    for k in range(num_levels):
+        nf = focal_samples if k == 0 else fine_samples
+        nfy, nfx = (nf, nf) if np.ndim(nf) == 0 else nf
+        fdx = focal_dx / scaling ** k
+        shift = fdx / 2.0
+        exs.append(prepare_executor(pupil_dx, pupil_samples, fdx, (nfy, nfx), wavelength, efl,
+                                    focal_shift=(shift, shift), kind=kind, rdtype=rdtype))
+        xf, yf = np.meshgrid(fftrange(nfx, rdtype) * fdx + shift, fftrange(nfy, rdtype) * fdx + shift)
+        xfs.append(xf)
+        yfs.append(yf)
+        radii.append(np.hypot(xf, yf))
+        halves.append(min(nfy, nfx) / 2.0 * fdx)
+    wins = []
+    for k in range(num_levels):
+        here = 1.0 if k == 0 else cumulative_window(radii[k], inner * halves[k], outer * halves[k])
+        nxt = 0.0 if k == num_levels - 1 else cumulative_window(radii[k], inner * halves[k + 1], outer * halves[k + 1])
+        wins.append(here - nxt)
+    return MultiResolutionExecutor(exs, wins, xfs, yfs)
+
+
+def to_fpm_and_back_multiresolution(w, fpm, mex, return_more=False):
+    """Sum over levels of unfocus(focus(w) * fpm(xf, yf) * window).  prysm/propagation/coronagraph.py:212-251."""
+    out, at, after = None, [], []
+    for ex, win, xf, yf in zip(mex.executors, mex.windows, mex.xf, mex.yf):
+        f = focus_dft(w, ex)
+        g = f * fpm(xf, yf) * win
+        c = unfocus_dft(g, ex)
+        out = c if out is None else out + c
+        at.append(f)
+        after.append(g)
+    return (out, at, after) if return_more else out
+
+
+def to_fpm_and_back_multiresolution_adjoint(g, fpm, mex, field_at_fpm=None):
+    """prysm/propagation/coronagraph.py:254-298.  Returns (Eabar, Ebbars, intermediates, fpm_bars or None)."""
+    out, Ebbars, inters, bars = None, [], [], []
+    for k, (ex, win, xf, yf) in enumerate(zip(mex.executors, mex.windows, mex.xf, mex.yf)):
+        m = fpm(xf, yf)
+        Eb = unfocus_dft_adjoint(g, ex)
+        it = adjoint_multiply(Eb, m * win)
+        c = focus_dft_adjoint(it, ex)
+        out = c if out is None else out + c
+        Ebbars.append(Eb)
+        inters.append(it)
+        if field_at_fpm is not None:
+            bars.append(adjoint_multiply(Eb, field_at_fpm[k] * win, real=not np.iscomplexobj(m)))
+    return out, Ebbars, inters, (bars if field_at_fpm is not None else None)
+
+
+# --------------------------------------------------------------------------------------
 # seeded synthetic pupil of SURVEY.md section 8(d)  (input generation; not on the hot path)
 # --------------------------------------------------------------------------------------
 
