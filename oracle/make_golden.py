@@ -162,7 +162,81 @@ def full():
     print('full_c3.npz written')
 
 
+def coronagraph():
+    """Adjoint twins + Lyot-coronagraph compositions -> coronagraph.npz."""
+    from prysm.polynomials import sum_of_2d_modes_adjoint
+    rng = np.random.default_rng(20260924)
+    g = {}
+    # elementwise adjoints
+    a = rng.random((18, 24))
+    a[2, 3] = 0
+    ph = rng.standard_normal((18, 24)) * 40
+    wf = Wavefront.from_amp_and_phase(a, ph, 0.55, 0.1)
+    bar = Wavefront(crand(rng, (18, 24)), 0.55, 0.1)
+    ibar = rng.random((18, 24))
+    g.update(ea_amp=a, ea_opd=ph, ea_bar=bar.data, ea_ibar=ibar,
+             ea_intensity_adjoint=wf.intensity_adjoint(ibar).data,
+             ea_phase=wf.from_amp_and_phase_adjoint_phase(bar),
+             ea_amp_nophase=wf.from_amp_and_phase_adjoint_amp(bar),
+             ea_amp_phase=wf.from_amp_and_phase_adjoint_amp(bar, phase=ph))
+    xg, yg = make_xy_grid((18, 24), dx=0.1)
+    g['ea_lens_adjoint'] = np.float64(Wavefront.thin_lens_adjoint(250.0, 0.55, xg, yg, bar))
+    # otf adjoints
+    pp = rng.random((20, 26))
+    D = otf.transform_psf(pp, 1.5)[0]
+    rb = rng.standard_normal((20, 26))
+    cb = crand(rng, (20, 26))
+    g.update(oa_psf=pp, oa_rbar=rb, oa_cbar=cb,
+             oa_mtf=otf.mtf_from_psf_adjoint(rb, data=D), oa_ptf=otf.ptf_from_psf_adjoint(rb, data=D),
+             oa_otf=otf.otf_from_psf_adjoint(cb, data=D),
+             oa_ee=otf.encircled_energy_adjoint([0.3, -1.2], dx=1.5, radius=[2.0, 7.5], data=D))
+    modes = rng.random((5, 18, 24))
+    g.update(ma_modes=modes, ma_out=sum_of_2d_modes_adjoint(modes, ibar))
+    # single-executor compositions
+    w = crand(rng, (28, 24))
+    gb = crand(rng, (28, 24))
+    lyot = rng.random((28, 24))
+    fpm_r = rng.random((20, 32))
+    fpm_c = crand(rng, (20, 32))
+    g.update(co_w=w, co_g=gb, co_lyot=lyot, co_fpm_real=fpm_r, co_fpm_cplx=fpm_c,
+             co_params=np.array([0.25, 0.8, 0.55, 20.0]))
+    for kind in ('mdft', 'czt'):
+        ex = propagation.prepare_executor(0.25, (28, 24), 0.8, (20, 32), 0.55, 20.0, kind=kind)
+        for fname, fpm in (('real', fpm_r), ('cplx', fpm_c)):
+            t = f'co_{kind}_{fname}_'
+            nxt, at, after = propagation.to_fpm_and_back(w, fpm, ex, return_more=True)
+            Ea, Eb, it, fb = propagation.to_fpm_and_back_adjoint(gb, fpm, ex, return_more=True, return_fpm_grad=True, field_at_fpm=at)
+            al, at2, af2, atl = propagation.babinet(w, lyot, fpm, ex, return_more=True)
+            ab, fbb, lb = propagation.babinet_adjoint(gb, lyot, fpm, ex, field_at_fpm=at2, field_at_lyot=atl,
+                                                      return_fpm_grad=True, return_lyot_grad=True)
+            g.update({t + 'next': nxt, t + 'at_fpm': at, t + 'after_fpm': after, t + 'Eabar': Ea, t + 'Ebbar': Eb,
+                      t + 'inter': it, t + 'fpm_bar': fb, t + 'bab_after_lyot': al, t + 'bab_at_fpm': at2,
+                      t + 'bab_at_lyot': atl, t + 'bab_abar': ab, t + 'bab_fpm_bar': fbb, t + 'bab_lyot_bar': lb})
+    # multi-resolution vortex stack (reference tests/test_propagation.py:544-556 geometry, 3 levels)
+    npup = 64
+    x = crand(rng, (npup, npup))
+    y = crand(rng, (npup, npup))
+    g.update(mr_x=x, mr_y=y, mr_params=np.array([0.1, 2.0, HeNe, 10.0]))
+    fpm = propagation.vortex_phase_mask(2)
+    for kind in ('mdft', 'czt'):
+        mr = propagation.prepare_multiresolution(0.1, npup, 2.0, 32, HeNe, 10.0, num_levels=3, fine_samples=32, kind=kind)
+        out, at, after = propagation.to_fpm_and_back_multiresolution(x, fpm, mr, return_more=True)
+        Ea, Ebs, its, fbs = propagation.to_fpm_and_back_multiresolution_adjoint(y, fpm, mr, return_more=True,
+                                                                                return_fpm_grad=True, field_at_fpm=at)
+        t = f'mr_{kind}_'
+        g.update({t + 'out': out, t + 'Eabar': Ea})
+        for k in range(3):
+            g.update({t + f'at{k}': at[k], t + f'after{k}': after[k], t + f'Ebbar{k}': Ebs[k], t + f'inter{k}': its[k],
+                      t + f'fpm_bar{k}': fbs[k]})
+            if kind == 'mdft':
+                g.update({f'mr_win{k}': mr.windows[k], f'mr_xf{k}': mr.xf[k], f'mr_yf{k}': mr.yf[k]})
+    g['mr_vortex1'] = fpm(mr.xf[1], mr.yf[1])
+    np.savez_compressed(os.path.join(OUT, 'coronagraph.npz'), **g)
+    print(f'coronagraph.npz written, {len(g)} arrays')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    small()
-    full()
+    which = sys.argv[1:] or ['small', 'full', 'coronagraph']   # name the fixtures to (re)write
+    for name in which:
+        {'small': small, 'full': full, 'coronagraph': coronagraph}[name]()
