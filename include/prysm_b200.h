@@ -202,6 +202,58 @@ int pb_encircled_energy(pb_handle_t h, int dtype, const void* mtf, int ny, int n
 int pb_moments(pb_handle_t h, int dtype, const void* data, int ny, int nx, double* sums_host,
                void* stream);
 
+
+/* ---- adjoint twins and Lyot-coronagraph compositions -----------------------
+ * masked multiply, the elementwise step of every composition in prysm/propagation/coronagraph.py and of
+ * _adjoint_multiply (prysm/propagation/_kernels.py:30-38):
+ *     out (+)= scale * (a - b) * f(m) * w
+ * a: complex; b: complex or NULL; m: real / complex (m_kind) or NULL; w: real or NULL.  flags (OR of pb_mask_flags):
+ * CONJ -> f = conj(m); ONE_MINUS -> f = 1 - m (Babinet complement, coronagraph.py:338); REAL_OUT -> out is a
+ * REAL array receiving the real part (the real=True branch of _adjoint_multiply); ACCUMULATE -> out += ... */
+typedef enum { PB_MASK_REAL = 0, PB_MASK_COMPLEX = 1 } pb_mask_kind;
+typedef enum { PB_MASK_CONJ = 1, PB_MASK_ONE_MINUS = 2, PB_MASK_REAL_OUT = 4, PB_MASK_ACCUMULATE = 8 } pb_mask_flags;
+int pb_mask_multiply(pb_handle_t h, int dtype, const void* a, const void* b, const void* m, int m_kind,
+                     int flags, const void* w, double scale, long long count, void* out, void* stream);
+/* adjoints of from_amp_and_phase (prysm/propagation/wavefront.py:172-242), kscale = 2*pi/(1e3*wavelength):
+ * mode 0: out (complex) = i*kscale*imag(bar*conj(field))              -- w.r.t. phase (the reference's prefix is
+ *         complex, so its result is purely imaginary; kept);
+ * mode 1: out (real) = real(bar*conj(field))/|field|, 0 where field=0 -- w.r.t. amplitude, phasor from the field;
+ * mode 2: out (real) = real(bar*conj(exp(i*kscale*opd)))              -- w.r.t. amplitude, phasor rebuilt from opd. */
+int pb_field_adjoint(pb_handle_t h, int dtype, int mode, const void* field, const void* bar,
+                     const void* opd, double kscale, long long count, void* out, void* stream);
+/* real array out = re (which 0) / im (1) / angle (2) / abs (3) of a complex array: Wavefront.real / .imag / .phase
+ * (prysm/propagation/wavefront.py:153-166). */
+int pb_component(pb_handle_t h, int dtype, int which, const void* in, long long count, void* out,
+                 void* stream);
+/* out_host[0..1] = sum w * a * conj(b) (w real or NULL; fp64 accumulation; synchronises the stream).
+ * The reduction of thin_lens_adjoint (prysm/propagation/wavefront.py:244-280) and of <x, y> adjoint checks. */
+int pb_dot(pb_handle_t h, int dtype, const void* a, const void* b, const void* w, long long count,
+           double* out_host, void* stream);
+/* out_host[2j..2j+1] = sum_n modes[j][n] * bar[n] for k real modes; bar real or complex (bar_complex).
+ * sum_of_2d_modes_adjoint (prysm/polynomials/fitting.py:40-57).  Synchronises the stream. */
+int pb_mode_projection(pb_handle_t h, int dtype, const void* modes, int k, long long count,
+                       const void* bar, int bar_complex, double* out_host, void* stream);
+/* k-space gradient of mtf (which=1, bar real) / ptf (2, bar real) / otf (4, bar complex) _from_psf_adjoint given
+ * the complex transform D (ny,nx), including the centre-normalisation term (prysm/otf.py:205-316); the caller
+ * finishes with transform_psf_adjoint (pb_fft2, dir=+1) and takes the real part. */
+int pb_otf_adjoint_seed(pb_handle_t h, int dtype, int which, const void* bar, const void* D, int ny,
+                        int nx, void* data_bar, void* stream);
+/* MTF-plane gradient of encircled_energy: mtf_bar = sum_r ee_bar[r]*r*J1(2 pi r nu)/nu*df^2, radii [mm] and
+ * ee_bar HOST arrays (prysm/otf.py:417-471). */
+int pb_encircled_energy_adjoint_seed(pb_handle_t h, int dtype, int ny, int nx, double df,
+                                     const double* radii_mm_host, const double* ee_bar_host, int nr,
+                                     void* mtf_bar, void* stream);
+/* out = exp(i*charge*atan2(yf, xf)) on real coordinate arrays: vortex_phase_mask
+ * (prysm/propagation/coronagraph.py:102-132). */
+int pb_vortex_phase(pb_handle_t h, int dtype, int charge, const void* xf, const void* yf,
+                    long long count, void* out, void* stream);
+/* one level of prepare_multiresolution (prysm/propagation/dft.py:155-167, 262-292): focal grids
+ * xf = (ix - nx/2)*fdx + shift, yf likewise, and the hand-off window
+ * taper(r; a0, b0) - taper(r; a1, b1), taper = 1 - smootherstep((r - a)/(b - a));
+ * a0 < 0 -> first term 1 (coarsest level); a1 < 0 -> second term 0 (finest level).  Any output may be NULL. */
+int pb_radial_window(pb_handle_t h, int dtype, int ny, int nx, double fdx, double shift, double a0,
+                     double b0, double a1, double b1, void* win, void* xf, void* yf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,8 @@ IN_COMPLEX, IN_REAL, IN_AMP_OPD = 0, 1, 2
 AMP_NONE, AMP_REAL, AMP_U8 = 0, 1, 2
 OUT_COMPLEX, OUT_INTENSITY, OUT_ACCUMULATE = 0, 1, 2
 OP_N, OP_T, OP_H, OP_C = 0, 1, 2, 3
+MASK_REAL, MASK_COMPLEX = 0, 1
+MASK_CONJ, MASK_ONE_MINUS, MASK_REAL_OUT, MASK_ACCUMULATE = 1, 2, 4, 8
 
 _vp, _i, _ll, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_double
 
@@ -48,6 +50,15 @@ SIGNATURES = {
     'pb_otf_normalize': (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'pb_encircled_energy': (_i, [_vp, _i, _vp, _i, _i, _d, C.POINTER(_d), _i, C.POINTER(_d), _vp]),
     'pb_moments': (_i, [_vp, _i, _vp, _i, _i, C.POINTER(_d), _vp]),
+    'pb_mask_multiply': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _d, _ll, _vp, _vp]),
+    'pb_field_adjoint': (_i, [_vp, _i, _i, _vp, _vp, _vp, _d, _ll, _vp, _vp]),
+    'pb_component': (_i, [_vp, _i, _i, _vp, _ll, _vp, _vp]),
+    'pb_dot': (_i, [_vp, _i, _vp, _vp, _vp, _ll, C.POINTER(_d), _vp]),
+    'pb_mode_projection': (_i, [_vp, _i, _vp, _i, _ll, _vp, _i, C.POINTER(_d), _vp]),
+    'pb_otf_adjoint_seed': (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    'pb_encircled_energy_adjoint_seed': (_i, [_vp, _i, _i, _i, _d, C.POINTER(_d), C.POINTER(_d), _i, _vp, _vp]),
+    'pb_vortex_phase': (_i, [_vp, _i, _i, _vp, _vp, _ll, _vp, _vp]),
+    'pb_radial_window': (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp, _vp]),
 }
 
 

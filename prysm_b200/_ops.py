@@ -375,6 +375,136 @@ def moments(data):
     return sums[0], sums[1], sums[2]
 
 
+def mask_multiply(a, m=None, *, b=None, w=None, conj=False, one_minus=False, real_out=False, scale=1.0, out=None):
+    """out (+)= scale * (a - b) * f(m) * w in one pass (pb_mask_multiply).  `a`, `b` complex; `m` real or complex
+    (f = conj(m) / 1 - m by flag); `w` real; real_out keeps the real part in a real tensor; a given `out` is
+    accumulated into."""
+    a = a.contiguous()
+    rd = _REAL_OF[a.dtype]
+
+    def same(t, name):
+        if t is not None and tuple(t.shape) != tuple(a.shape):
+            raise ValueError(f'shape mismatch: field {tuple(a.shape)} vs {name} {tuple(t.shape)}')
+        return t
+    kind = capi.MASK_REAL
+    if m is not None:
+        m = same(asdevice(m), 'mask')
+        if m.is_complex():
+            kind, m = capi.MASK_COMPLEX, m.to(a.dtype).contiguous()
+        else:
+            m = m.to(rd).contiguous()
+    b = None if b is None else same(b, 'subtrahend').to(a.dtype).contiguous()
+    w = None if w is None else same(asdevice(w), 'window').to(rd).contiguous()
+    flags = (capi.MASK_CONJ if conj else 0) | (capi.MASK_ONE_MINUS if one_minus else 0) | \
+            (capi.MASK_REAL_OUT if real_out else 0)
+    if out is None:
+        out = torch.empty(a.shape, dtype=rd if real_out else a.dtype, device=a.device)
+    else:
+        flags |= capi.MASK_ACCUMULATE
+    h, st = _ctx(a)
+    h.check(lib.pb_mask_multiply(h.ptr, _CODE[a.dtype], _p(a), _p(b), _p(m), kind, flags, _p(w), float(scale),
+                                 a.numel(), _p(out), st))
+    return out
+
+
+def field_adjoint(mode, field, bar, opd, kscale):
+    """Adjoints of from_amp_and_phase (pb_field_adjoint): mode 0 phase (complex out), 1 / 2 amplitude (real out)."""
+    bar = bar.contiguous()
+    rd = _REAL_OF[bar.dtype]
+    field = None if field is None else field.to(bar.dtype).contiguous()
+    opd = None if opd is None else asdevice(opd).to(rd).contiguous()
+    out = torch.empty(bar.shape, dtype=bar.dtype if mode == 0 else rd, device=bar.device)
+    h, st = _ctx(bar)
+    h.check(lib.pb_field_adjoint(h.ptr, _CODE[bar.dtype], int(mode), _p(field), _p(bar), _p(opd), float(kscale),
+                                 bar.numel(), _p(out), st))
+    return out
+
+
+def component(which, field):
+    """re / im / angle / abs of a complex tensor as a contiguous real tensor (pb_component)."""
+    field = field.contiguous()
+    out = torch.empty(field.shape, dtype=_REAL_OF[field.dtype], device=field.device)
+    h, st = _ctx(field)
+    h.check(lib.pb_component(h.ptr, _CODE[field.dtype], {'real': 0, 'imag': 1, 'angle': 2, 'abs': 3}[which], _p(field),
+                             field.numel(), _p(out), st))
+    return out
+
+
+def dot(a, b, w=None):
+    """sum w * a * conj(b) as a Python complex (pb_dot; fp64 accumulation)."""
+    a = a.contiguous()
+    b = b.to(a.dtype).contiguous()
+    if a.shape != b.shape:
+        raise ValueError(f'shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}')
+    w = None if w is None else asdevice(w).to(_REAL_OF[a.dtype]).contiguous()
+    out = (C.c_double * 2)()
+    h, st = _ctx(a)
+    h.check(lib.pb_dot(h.ptr, _CODE[a.dtype], _p(a), _p(b), _p(w), a.numel(), out, st))
+    return complex(out[0], out[1])
+
+
+def mode_projection(modes, bar):
+    """tensordot(modes(k, m, n), bar(m, n)) over the trailing axes (pb_mode_projection) -> host array (k,)."""
+    modes = modes.contiguous()
+    k = modes.shape[0]
+    cplx = bar.is_complex()
+    bar = bar.to(_CPLX_OF[modes.dtype] if cplx else modes.dtype).contiguous()
+    if tuple(bar.shape) != tuple(modes.shape[1:]):
+        raise ValueError(f'shape mismatch: modes {tuple(modes.shape)} vs gradient {tuple(bar.shape)}')
+    out = (C.c_double * (2 * k))()
+    h, st = _ctx(modes)
+    h.check(lib.pb_mode_projection(h.ptr, _CODE[modes.dtype], _p(modes), k, bar.numel(), _p(bar), int(cplx), out, st))
+    v = np.array(out[:]).reshape(k, 2)
+    return v[:, 0] + 1j * v[:, 1] if cplx else v[:, 0].copy()
+
+
+def otf_adjoint_seed(which, bar, D):
+    """k-space gradient of mtf (1) / ptf (2) / otf (4) _from_psf_adjoint (pb_otf_adjoint_seed)."""
+    D = D.contiguous()
+    ny, nx = D.shape
+    bar = asdevice(bar)
+    bar = bar.to(D.dtype if which == 4 else _REAL_OF[D.dtype]).contiguous()
+    if tuple(bar.shape) != (ny, nx):
+        raise ValueError(f'shape mismatch: gradient {tuple(bar.shape)} vs transform {(ny, nx)}')
+    out = torch.empty_like(D)
+    h, st = _ctx(D)
+    h.check(lib.pb_otf_adjoint_seed(h.ptr, _CODE[D.dtype], int(which), _p(bar), _p(D), ny, nx, _p(out), st))
+    return out
+
+
+def encircled_energy_adjoint_seed(shape, df, radii_mm, ee_bar, rdtype, dev):
+    ny, nx = shape
+    r, rp = _darr(radii_mm)
+    b, bp = _darr(ee_bar)
+    if len(r) != len(b):
+        raise ValueError('one gradient value per radius is required')
+    out = torch.empty((ny, nx), dtype=rdtype, device=dev)
+    h, st = _ctx(out)
+    h.check(lib.pb_encircled_energy_adjoint_seed(h.ptr, _CODE[rdtype], ny, nx, float(df), rp, bp, len(r), _p(out), st))
+    return out
+
+
+def vortex_phase(charge, xf, yf):
+    xf = xf.contiguous()
+    yf = yf.to(xf.dtype).contiguous()
+    out = torch.empty(xf.shape, dtype=_CPLX_OF[xf.dtype], device=xf.device)
+    h, st = _ctx(xf)
+    h.check(lib.pb_vortex_phase(h.ptr, _CODE[xf.dtype], int(charge), _p(xf), _p(yf), xf.numel(), _p(out), st))
+    return out
+
+
+def radial_window(shape, fdx, shift, here, nxt, rdtype, dev):
+    """(window, xf, yf) of one multi-resolution level (pb_radial_window); here / nxt = (a, b) or None."""
+    ny, nx = shape
+    win, xf, yf = (torch.empty((ny, nx), dtype=rdtype, device=dev) for _ in range(3))
+    a0, b0 = here if here is not None else (-1.0, 0.0)
+    a1, b1 = nxt if nxt is not None else (-1.0, 0.0)
+    h, st = _ctx(win)
+    h.check(lib.pb_radial_window(h.ptr, _CODE[rdtype], ny, nx, float(fdx), float(shift), float(a0), float(b0), float(a1),
+                                 float(b1), _p(win), _p(xf), _p(yf), st))
+    return win, xf, yf
+
+
 def launch_count(dev=None):
     dev = device() if dev is None else torch.device(dev)
     return capi.launch_count(dev.index)

@@ -107,6 +107,12 @@ class MDFT:
         self._tc = None
         if cd == torch.complex64 and use_tensor_cores and _ops.mdft_tc_supported(My, Ny, Mx, Nx):
             self._tc = _ops.mdft_tc_expand(self.Ex) + _ops.mdft_tc_expand(self.Ey)
+        # the adjoint Ey^H @ g @ conj(Ex) is the same two-GEMM form with the bases Ey^H = basis(y, fy, -sign)
+        # and Ex^H, so it runs on the tensor cores too when the swapped shape allows
+        self._tc_adj = None
+        if cd == torch.complex64 and use_tensor_cores and _ops.mdft_tc_supported(Ny, My, Nx, Mx):
+            self._tc_adj = (_ops.mdft_tc_expand(_ops.mdft_basis(x, fx, -sign, cd, dev))
+                            + _ops.mdft_tc_expand(_ops.mdft_basis(y, fy, -sign, cd, dev)))
 
     def __call__(self, ary):
         ary = _prep(ary, self.Ey.dtype)
@@ -115,8 +121,10 @@ class MDFT:
         return _ops.mdft_apply(self.Ey, self.Ex, ary, self.norm, False, self._forward_left_first)
 
     def adjoint(self, grad):
-        return _ops.mdft_apply(self.Ey, self.Ex, _prep(grad, self.Ey.dtype), self.norm, True,
-                               self._adjoint_left_first)
+        grad = _prep(grad, self.Ey.dtype)
+        if self._tc_adj is not None:
+            return _ops.mdft_tc_apply(*self._tc_adj, grad, self.norm)
+        return _ops.mdft_apply(self.Ey, self.Ex, grad, self.norm, True, self._adjoint_left_first)
 
     def nbytes(self):
         return self.Ex.numel() * self.Ex.element_size() + self.Ey.numel() * self.Ey.element_size()

@@ -24,23 +24,35 @@ _PROPAGATION_FUNCS = (
     'angular_spectrum', 'angular_spectrum_adjoint', 'angular_spectrum_transfer_function',
     'prepare_executor', 'coordinates_for_focus', 'focus_dft', 'unfocus_dft', 'focus_dft_adjoint', 'unfocus_dft_adjoint',
 )
+_CORONAGRAPH_FUNCS = (
+    'to_fpm_and_back', 'to_fpm_and_back_adjoint', 'to_fpm_and_back_multiresolution',
+    'to_fpm_and_back_multiresolution_adjoint', 'babinet', 'babinet_adjoint', 'vortex_phase_mask',
+)
 _TARGETS = {
     'prysm.propagation.fft': {n: getattr(_prop, n) for n in ('focus', 'unfocus', 'focus_adjoint', 'unfocus_adjoint')},
     'prysm.propagation.angular_spectrum': {n: getattr(_prop, n) for n in (
         'angular_spectrum', 'angular_spectrum_adjoint', 'angular_spectrum_transfer_function')},
     'prysm.propagation.dft': {**{n: getattr(_prop, n) for n in (
         'prepare_executor', 'coordinates_for_focus', 'focus_dft', 'unfocus_dft', 'focus_dft_adjoint', 'unfocus_dft_adjoint')},
-        'MDFT': _ft.MDFT, 'CZT': _ft.CZT, 'FFTDFT': _ft.FFTDFT},
-    'prysm.propagation.wavefront': {**{n: getattr(_prop, n) for n in _PROPAGATION_FUNCS if n not in (
-        'angular_spectrum_transfer_function', 'coordinates_for_focus')}, 'pad2d': _ft.pad2d, 'crop_center': _ft.crop_center},
-    'prysm.propagation': {n: getattr(_prop, n) for n in _PROPAGATION_FUNCS},
+        'MDFT': _ft.MDFT, 'CZT': _ft.CZT, 'FFTDFT': _ft.FFTDFT,
+        'prepare_multiresolution': _prop.prepare_multiresolution, 'MultiResolutionExecutor': _prop.MultiResolutionExecutor},
+    'prysm.propagation.coronagraph': {n: getattr(_prop, n) for n in _CORONAGRAPH_FUNCS},
+    'prysm.propagation.wavefront': {**{n: getattr(_prop, n) for n in _PROPAGATION_FUNCS + _CORONAGRAPH_FUNCS if n not in (
+        'angular_spectrum_transfer_function', 'coordinates_for_focus', 'vortex_phase_mask')},
+        'prepare_multiresolution': _prop.prepare_multiresolution, 'pad2d': _ft.pad2d, 'crop_center': _ft.crop_center},
+    'prysm.propagation': {**{n: getattr(_prop, n) for n in _PROPAGATION_FUNCS + _CORONAGRAPH_FUNCS},
+                          'prepare_multiresolution': _prop.prepare_multiresolution,
+                          'MultiResolutionExecutor': _prop.MultiResolutionExecutor},
     'prysm.fttools': {'MDFT': _ft.MDFT, 'CZT': _ft.CZT, 'FFTDFT': _ft.FFTDFT, 'pad2d': _ft.pad2d,
                       'crop_center': _ft.crop_center},
     'prysm.otf': {n: getattr(_otf, n) for n in (
-        'transform_psf', 'transform_psf_adjoint', 'mtf_from_psf', 'ptf_from_psf', 'otf_from_psf', 'mtf_ptf_otf_from_psf')},
+        'transform_psf', 'transform_psf_adjoint', 'mtf_from_psf', 'ptf_from_psf', 'otf_from_psf', 'mtf_ptf_otf_from_psf',
+        'mtf_from_psf_adjoint', 'ptf_from_psf_adjoint', 'otf_from_psf_adjoint', 'encircled_energy',
+        'encircled_energy_adjoint')},
     'prysm.psf': {'centroid': _psf.centroid},
-    'prysm.polynomials': {'sum_of_2d_modes': _poly.sum_of_2d_modes},
-    'prysm.polynomials.fitting': {'sum_of_2d_modes': _poly.sum_of_2d_modes},
+    'prysm.polynomials': {'sum_of_2d_modes': _poly.sum_of_2d_modes, 'sum_of_2d_modes_adjoint': _poly.sum_of_2d_modes_adjoint},
+    'prysm.polynomials.fitting': {'sum_of_2d_modes': _poly.sum_of_2d_modes,
+                                  'sum_of_2d_modes_adjoint': _poly.sum_of_2d_modes_adjoint},
 }
 
 _saved = {}  # (module name, attribute) -> original

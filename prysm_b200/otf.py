@@ -64,6 +64,56 @@ def mtf_ptf_otf_from_psf(psf, dx=None, return_more=False):
     return out + (data,) if return_more else out
 
 
+def _forward_data(psf, dx, data):
+    if data is None:
+        data, _ = transform_psf(psf, dx)
+    return _ops.ascomplex(_ops.asdevice(data))
+
+
+def mtf_from_psf_adjoint(mtf_bar, psf=None, dx=None, data=None):
+    """Gradient at the PSF plane of a gradient on the centre-normalised MTF: one seed kernel (modulus +
+    normalisation terms) and the adjoint transform (prysm/otf.py:205-242)."""
+    seed = _ops.otf_adjoint_seed(1, mtf_bar, _forward_data(psf, dx, data))
+    return transform_psf_adjoint(seed).real
+
+
+def ptf_from_psf_adjoint(ptf_bar, psf=None, dx=None, data=None):
+    """prysm/otf.py:245-279."""
+    seed = _ops.otf_adjoint_seed(2, ptf_bar, _forward_data(psf, dx, data))
+    return transform_psf_adjoint(seed).real
+
+
+def otf_from_psf_adjoint(otf_bar, psf=None, dx=None, data=None):
+    """prysm/otf.py:282-316."""
+    seed = _ops.otf_adjoint_seed(4, _ops.ascomplex(_ops.asdevice(otf_bar)), _forward_data(psf, dx, data))
+    return transform_psf_adjoint(seed).real
+
+
+def encircled_energy_adjoint(ee_bar, psf=None, dx=None, radius=None, data=None):
+    """Encircled energy is linear in the MTF: the per-radius gradients fold into one MTF-plane gradient (one
+    kernel), then mtf_from_psf_adjoint (prysm/otf.py:417-471)."""
+    import numbers
+    import numpy as np
+    if data is not None:
+        if dx is None:
+            raise ValueError('dx is None: dx must be provided to set the frequency grid')
+        data = _ops.ascomplex(_ops.asdevice(data))
+        dxv = dx
+    else:
+        arr, dxv = _unwrap_psf(psf, dx)
+        data, _ = transform_psf(arr, dxv)
+    shape = tuple(data.shape)
+    df = 1000 / (shape[0] * dxv)
+    if isinstance(radius, numbers.Number):
+        radius, ee_bar = (radius,), (ee_bar,)
+    radii = np.asarray(list(radius), dtype=np.float64) / 1e3
+    bars = np.asarray(list(ee_bar), dtype=np.float64)[:len(radii)]
+    radii = radii[:len(bars)]                                   # zip() semantics of the reference loop
+    rd = data.real.dtype
+    mtf_bar = _ops.encircled_energy_adjoint_seed(shape, df, radii, bars, rd, data.device)
+    return mtf_from_psf_adjoint(mtf_bar, data=data)
+
+
 def encircled_energy(psf, dx, radius, return_more=False):
     """Baliga & Cohn encircled energy at `radius` [um] (scalar or iterable) from the MTF of the PSF
     (prysm/otf.py:346-387): one reduction kernel per call covers all radii."""

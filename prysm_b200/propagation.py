@@ -20,6 +20,10 @@ from ._capi import OUT_COMPLEX, OUT_INTENSITY, OUT_ACCUMULATE
 from ._richdata import RichData
 from .conf import config
 from .fttools import pad2d, crop_center, MDFT, CZT, FFTDFT
+from .coronagraph import (  # noqa: F401  (re-exported like prysm/propagation/__init__.py)
+    to_fpm_and_back, to_fpm_and_back_adjoint, to_fpm_and_back_multiresolution,
+    to_fpm_and_back_multiresolution_adjoint, babinet, babinet_adjoint, vortex_phase_mask,
+)
 
 
 # ------------------------------------------------------------------------------------------
@@ -218,6 +222,53 @@ def unit_cell_focal_grid(pupil_dx, pupil_diameter, wavelength, efl, Q=2):
     return wavelength * efl / pupil_dx / focal_samples, focal_samples
 
 
+class MultiResolutionExecutor:
+    """Per-level executors (coarsest first), real partition-of-unity windows and focal coordinate grids [um]
+    (prysm/propagation/dft.py:170-209).  Windows and grids are device tensors."""
+
+    __slots__ = ('executors', 'windows', 'xf', 'yf')
+
+    def __init__(self, executors, windows, xf, yf):
+        self.executors = executors
+        self.windows = windows
+        self.xf = xf
+        self.yf = yf
+
+    def __len__(self):
+        return len(self.executors)
+
+
+def prepare_multiresolution(pupil_dx, pupil_samples, focal_dx, focal_samples, wavelength, efl, num_levels, scaling=4.0,
+                            fine_samples=None, window=(0.2, 0.7), kind='mdft'):
+    """Stack of executors zooming into the focal origin by `scaling` per level, each shifted by half a focal
+    sample, plus the telescoping hand-off windows (prysm/propagation/dft.py:212-294).  Grids and window of a
+    level come from one kernel."""
+    if fine_samples is None:
+        fine_samples = focal_samples
+    inner, outer = window
+    geo = []
+    for k in range(num_levels):
+        nf = focal_samples if k == 0 else fine_samples
+        if not isinstance(nf, Iterable):
+            nf = (nf, nf)
+        nfy, nfx = nf
+        fdx = focal_dx / scaling ** k
+        geo.append((nfy, nfx, fdx, min(nfy, nfx) / 2.0 * fdx))
+    executors, windows, xfs, yfs = [], [], [], []
+    dev = _ops.device()
+    for k, (nfy, nfx, fdx, half) in enumerate(geo):
+        shift = fdx / 2.0
+        executors.append(prepare_executor(pupil_dx, pupil_samples, fdx, (nfy, nfx), wavelength, efl,
+                                          focal_shift=(shift, shift), kind=kind))
+        here = None if k == 0 else (inner * half, outer * half)
+        nxt = None if k == num_levels - 1 else (inner * geo[k + 1][3], outer * geo[k + 1][3])
+        win, xf, yf = _ops.radial_window((nfy, nfx), fdx, shift, here, nxt, config.real_dtype, dev)
+        windows.append(win)
+        xfs.append(xf)
+        yfs.append(yf)
+    return MultiResolutionExecutor(executors, windows, xfs, yfs)
+
+
 def focus_dft(wavefunction, executor):
     """prysm/propagation/dft.py:297-313."""
     return executor(wavefunction)
@@ -258,6 +309,13 @@ def unfocus_fixed_sampling(wavefunction, input_dx, prop_dist, wavelength, output
 # ------------------------------------------------------------------------------------------
 # object API (prysm/propagation/wavefront.py)
 # ------------------------------------------------------------------------------------------
+
+def _field_data(field):
+    """Array of a Wavefront-like, anything else unchanged (prysm/propagation/wavefront.py:28-32)."""
+    if isinstance(field, Wavefront):
+        return field.data
+    return field
+
 
 class Wavefront:
     """(Complex) representation of a wavefront (prysm/propagation/wavefront.py:35-56)."""
@@ -316,8 +374,59 @@ class Wavefront:
         """abs(w)^2 as RichData (prysm/propagation/wavefront.py:147-151)."""
         return RichData(_ops.intensity(self.data), self.dx, self.wavelength)
 
+    @property
+    def phase(self):
+        """angle(w) (prysm/propagation/wavefront.py:153-156)."""
+        return RichData(_ops.component('angle', self.data), self.dx, self.wavelength)
+
+    @property
+    def real(self):
+        """re(w) (prysm/propagation/wavefront.py:158-161)."""
+        return RichData(_ops.component('real', self.data), self.dx, self.wavelength)
+
+    @property
+    def imag(self):
+        """im(w) (prysm/propagation/wavefront.py:163-166)."""
+        return RichData(_ops.component('imag', self.data), self.dx, self.wavelength)
+
     def copy(self):
         return Wavefront(self.data.clone(), self.wavelength, self.dx, self.space)
+
+    # ---- adjoints of the elementwise constructors (prysm/propagation/wavefront.py:172-298)
+    def from_amp_and_phase_adjoint_phase(self, wf_bar):
+        """prefix * imag(gbar * conj(g)).  The reference multiplies by the COMPLEX prefix i*2*pi/(1e3*wvl)
+        (wavefront.py:187-188), so the result is a purely imaginary array; kept for parity."""
+        return _ops.field_adjoint(0, self.data, _field(_field_data(wf_bar)), None, phase_prefix(self.wavelength).imag)
+
+    def from_amp_and_phase_adjoint_amp(self, wf_bar, phase=None):
+        """real(gbar * conj(S)), S the unit phasor: rebuilt from `phase` [nm] when given, else P/|P| with zero
+        gradient where the amplitude vanishes (prysm/propagation/wavefront.py:190-225)."""
+        bar = _field(_field_data(wf_bar))
+        k = phase_prefix(self.wavelength).imag
+        if phase is not None:
+            return _ops.field_adjoint(2, None, bar, _ops.asdevice(phase), k)
+        return _ops.field_adjoint(1, self.data, bar, None, k)
+
+    def phase_screen_adjoint_phase(self, wf_bar):
+        """prysm/propagation/wavefront.py:227-242."""
+        return self.from_amp_and_phase_adjoint_phase(wf_bar)
+
+    @classmethod
+    def thin_lens_adjoint(cls, f, wavelength, x, y, wf_bar):
+        """Gradient w.r.t. the focal length: pi/(w f^2) * sum(r^2 * imag(Lbar * conj(L))) as one weighted-dot
+        reduction (prysm/propagation/wavefront.py:244-280)."""
+        L_bar = _field(_field_data(wf_bar))
+        L = cls.thin_lens(f, wavelength, x, y).data
+        x, y = _ops.asdevice(x), _ops.asdevice(y)
+        rsq = x * x + y * y                                   # coordinate prep, as in thin_lens
+        w = wavelength / 1e3
+        return math.pi / (w * f * f) * _ops.dot(L_bar, L, rsq).imag
+
+    def intensity_adjoint(self, intensity_bar):
+        """Gbar = 2 * Ibar * E (prysm/propagation/wavefront.py:282-298)."""
+        ibar = intensity_bar.data if isinstance(intensity_bar, (RichData, Wavefront)) else intensity_bar
+        ibar = _ops.asdevice(ibar)
+        return Wavefront(_ops.mask_multiply(self.data, ibar, scale=2.0), self.wavelength, self.dx, self.space)
 
     def pad2d(self, Q, value=0, mode='constant', out_shape=None, inplace=True):
         """prysm/propagation/wavefront.py:300-332."""
@@ -347,7 +456,7 @@ class Wavefront:
             if not all(criteria):
                 raise ValueError('all physicality criteria not met: sample spacing, shape, wavelength, or space different.')
             data = _ops.binary(op, self.data, other.data, reverse)
-        elif isinstance(other, torch.Tensor):
+        elif isinstance(other, (torch.Tensor, np.ndarray)):      # host arrays are uploaded like everywhere else
             data = _ops.binary(op, self.data, _ops.asdevice(other), reverse)
         elif isinstance(other, numbers.Number):
             data = _ops.binary(op, self.data, other, reverse)
@@ -477,6 +586,81 @@ class Wavefront:
             raise ValueError('can only apply adjoint from a pupil to psf plane')
         data = unfocus_dft_adjoint(self.data, executor)
         return Wavefront(dx=executor.focal_dx, cmplx_field=data, wavelength=self.wavelength, space='psf')
+
+    # ---- Lyot-coronagraph compositions (prysm/propagation/wavefront.py:643-677, 758-1038)
+    def prepare_multiresolution(self, efl, focal_dx, focal_samples, num_levels, scaling=4.0, fine_samples=None,
+                                window=(0.2, 0.7), kind='mdft'):
+        if self.space != 'pupil':
+            raise ValueError('multiresolution propagation begins at a pupil plane')
+        return prepare_multiresolution(pupil_dx=self.dx, pupil_samples=self._shape(), focal_dx=focal_dx,
+                                       focal_samples=focal_samples, wavelength=self.wavelength, efl=efl,
+                                       num_levels=num_levels, scaling=scaling, fine_samples=fine_samples,
+                                       window=window, kind=kind)
+
+    def _pupil(self, data):
+        return Wavefront(data, self.wavelength, self.dx, self.space)
+
+    def _psf(self, data, executor):
+        return Wavefront(data, self.wavelength, executor.focal_dx, 'psf')
+
+    def to_fpm_and_back(self, fpm, executor, return_more=False):
+        pak = to_fpm_and_back(self.data, fpm=_field_data(fpm), executor=executor, return_more=return_more)
+        if return_more:
+            nxt, at_fpm, after_fpm = pak
+            return self._pupil(nxt), self._psf(at_fpm, executor), self._psf(after_fpm, executor)
+        return self._pupil(pak)
+
+    def to_fpm_and_back_adjoint(self, fpm, executor, return_more=False, return_fpm_grad=False, field_at_fpm=None):
+        pak = to_fpm_and_back_adjoint(self.data, fpm=_field_data(fpm), executor=executor, return_more=return_more,
+                                      return_fpm_grad=return_fpm_grad, field_at_fpm=_field_data(field_at_fpm))
+        if not (return_more or return_fpm_grad):
+            return self._pupil(pak)
+        return (self._pupil(pak[0]),) + tuple(self._psf(p, executor) for p in pak[1:])
+
+    def to_fpm_and_back_multiresolution(self, fpm, executor, return_more=False):
+        if self.space != 'pupil':
+            raise ValueError('can only propagate from a pupil to psf plane')
+        pak = to_fpm_and_back_multiresolution(self.data, fpm, executor, return_more=return_more)
+        if not return_more:
+            return self._pupil(pak)
+        out, at_fpm, after_fpm = pak
+        return (self._pupil(out), [self._psf(f, ex) for f, ex in zip(at_fpm, executor.executors)],
+                [self._psf(f, ex) for f, ex in zip(after_fpm, executor.executors)])
+
+    def to_fpm_and_back_multiresolution_adjoint(self, fpm, executor, return_more=False, return_fpm_grad=False,
+                                                field_at_fpm=None):
+        if field_at_fpm is not None:
+            field_at_fpm = [_field_data(f) for f in field_at_fpm]
+        pak = to_fpm_and_back_multiresolution_adjoint(self.data, fpm, executor, return_more=return_more,
+                                                      return_fpm_grad=return_fpm_grad, field_at_fpm=field_at_fpm)
+        if not (return_more or return_fpm_grad):
+            return self._pupil(pak)
+        return (self._pupil(pak[0]),) + tuple([self._psf(f, ex) for f, ex in zip(fields, executor.executors)]
+                                               for fields in pak[1:])
+
+    def babinet(self, lyot, fpm, executor, return_more=False):
+        pak = babinet(self.data, lyot=_field_data(lyot), fpm=_field_data(fpm), executor=executor,
+                      return_more=return_more)
+        if return_more:
+            after_lyot, at_fpm, after_fpm, at_lyot = pak
+            return (self._pupil(after_lyot), self._psf(at_fpm, executor), self._psf(after_fpm, executor),
+                    self._pupil(at_lyot))
+        return self._pupil(pak)
+
+    def babinet_adjoint(self, lyot, fpm, executor, field_at_fpm=None, field_at_lyot=None, return_fpm_grad=False,
+                        return_lyot_grad=False):
+        pak = babinet_adjoint(self.data, lyot=_field_data(lyot), fpm=_field_data(fpm), executor=executor,
+                              field_at_fpm=_field_data(field_at_fpm), field_at_lyot=_field_data(field_at_lyot),
+                              return_fpm_grad=return_fpm_grad, return_lyot_grad=return_lyot_grad)
+        if not (return_fpm_grad or return_lyot_grad):
+            return self._pupil(pak)
+        pak = list(pak)
+        out = [self._pupil(pak.pop(0))]
+        if return_fpm_grad:
+            out.append(self._psf(pak.pop(0), executor))
+        if return_lyot_grad:
+            out.append(self._pupil(pak.pop(0)))
+        return tuple(out)
 
     # legacy spellings named by BASELINE.json
     def focus_fixed_sampling(self, efl, dx, samples, shift=(0, 0), method='mdft'):

@@ -37,6 +37,10 @@ def test_rebinding_round_trip(prysm_pkg):
         assert pf.MDFT is bf.MDFT and po.mtf_from_psf is bo.mtf_from_psf
         import prysm.propagation.dft as pd
         assert pd.MDFT is bf.MDFT and pd.CZT is bf.CZT                  # prepare_executor's constructors
+        import prysm.propagation.coronagraph as pc
+        assert pc.babinet is bp.babinet and pw.to_fpm_and_back is bp.to_fpm_and_back   # Wavefront.babinet resolves pw.*
+        assert pp.prepare_multiresolution is bp.prepare_multiresolution and pp.vortex_phase_mask is bp.vortex_phase_mask
+        assert po.encircled_energy_adjoint is bo.encircled_energy_adjoint
     finally:
         mathops.set_backend_to_defaults()
     assert (pp.focus, pw.focus, pw.angular_spectrum, pf.MDFT, po.mtf_from_psf, pw.prepare_executor) == orig
