@@ -200,6 +200,33 @@ for prec, rdt, cdt, eps in ((64, np.float64, np.complex128, 1e-13), (32, np.floa
             check(tag + f'{kind} multires inter[{k}]', got[2][k], refa[2][k], eps)
             check(tag + f'{kind} multires fpm_bar[{k}]', got[3][k], refa[3][k], eps)
 
+    # ---- pupil synthesis by recurrence (rank 3)
+    from prysm import coordinates as pcoord, geometry as pgeom
+    from prysm.polynomials import jacobi as pjacobi, jacobi_seq as pjacobi_seq, zernike_nm as pz_nm, zernike_sum as pz_sum
+    for shp, kw in (((9, 12), dict(dx=0.25)), (16, dict(diameter=2.0))):
+        xr, yr = pcoord.make_xy_grid(shp, **kw)
+        xo, yo = O.make_xy_grid(shp, dtype=rdt, **kw)
+        check(tag + f'make_xy_grid {shp} x', xo, xr)
+        check(tag + f'make_xy_grid {shp} y', yo, yr)
+    rr, tr = pcoord.cart_to_polar(xr, yr)
+    ro, to = O.cart_to_polar(xo, yo)
+    check(tag + 'cart_to_polar r', ro, rr)
+    check(tag + 'cart_to_polar t', to, tr)
+    check(tag + 'circle', O.circle(0.7, ro), pgeom.circle(0.7, rr))
+    check(tag + 'antialias', O.antialias(ro - 0.7, 2.0 / 16), pgeom.antialias(rr - rdt(0.7), 2.0 / 16), eps)
+    xs = np.linspace(-1, 1, 41).astype(rdt)
+    for (al, be) in ((0, 0), (0, 3), (1.5, 0.5), (-0.5, -0.5)):
+        check(tag + f'jacobi_seq a={al} b={be}', O.jacobi_seq([0, 1, 2, 5, 9], al, be, xs), pjacobi_seq([0, 1, 2, 5, 9], al, be, xs), eps)
+        check(tag + f'jacobi n=7 a={al} b={be}', O.jacobi(7, al, be, xs), pjacobi(7, al, be, xs), eps)
+    nms = [noll_to_nm(j) for j in range(1, 38)]
+    rn = ro / ro.max()
+    for nrm in (True, False):
+        check(tag + f'zernike_nm_seq norm={nrm}', O.zernike_nm_seq(nms, rn, to, nrm), zernike_nm_seq(nms, rn, tr, norm=nrm), eps * 10)
+    check(tag + 'zernike_nm (single) == seq', O.zernike_nm_seq([(4, -2)], rn, to)[0], pz_nm(4, -2, rn, tr), eps * 10)
+    cz = rng.standard_normal(37).astype(rdt)
+    cz[3] = 0
+    check(tag + 'zernike_sum', O.zernike_sum(cz, nms, xo, yo), pz_sum(cz, nms, xr, yr), eps * 10)
+
 # pupil builder (fp64 maths, cast at the end)
 for j in range(1, 60):
     assert O.noll_to_nm(j) == noll_to_nm(j), j

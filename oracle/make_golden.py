@@ -235,8 +235,39 @@ def coronagraph():
     print(f'coronagraph.npz written, {len(g)} arrays')
 
 
+def synthesis():
+    """Pupil synthesis by recurrence -> synthesis.npz."""
+    from prysm import geometry
+    from prysm.polynomials import jacobi_seq, zernike_nm, zernike_sum
+    rng = np.random.default_rng(20260925)
+    g = {}
+    x, y = make_xy_grid((33, 40), dx=0.06)
+    r, t = cart_to_polar(x, y)
+    g.update(grid_x=x, grid_y=y, grid_r=r, grid_t=t, circle=geometry.circle(1.0, r),
+             grey=geometry.antialias(geometry.circle_sdf(1.0, r), 0.06))
+    xd, yd = make_xy_grid(32, diameter=2.0)
+    g.update(grid_xd=xd, grid_yd=yd)
+    xs = np.linspace(-1, 1, 65)
+    g['jac_x'] = xs
+    for i, (al, be) in enumerate(((0, 0), (0, 3), (1.5, 0.5), (-0.5, -0.5))):
+        g[f'jac{i}_ab'] = np.array([al, be], dtype=np.float64)
+        g[f'jac{i}'] = jacobi_seq([0, 1, 2, 5, 9, 14], al, be, xs)
+    nms = [noll_to_nm(j) for j in range(1, 38)]
+    rn = r / 1.2
+    g['z_nms'] = np.array(nms)
+    g['z_seq_norm'] = zernike_nm_seq(nms, rn, t, norm=True)
+    g['z_seq_raw'] = zernike_nm_seq(nms, rn, t, norm=False)
+    g['z_single'] = zernike_nm(5, -3, rn, t)
+    c = rng.standard_normal(37) * 20
+    c[4] = 0
+    g['z_coefs'] = c
+    g['z_sum'] = zernike_sum(c, nms, x / 1.2, y / 1.2)
+    np.savez_compressed(os.path.join(OUT, 'synthesis.npz'), **g)
+    print(f'synthesis.npz written, {len(g)} arrays')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['small', 'full', 'coronagraph']   # name the fixtures to (re)write
+    which = sys.argv[1:] or ['small', 'full', 'coronagraph', 'synthesis']   # name the fixtures to (re)write
     for name in which:
-        {'small': small, 'full': full, 'coronagraph': coronagraph}[name]()
+        {'small': small, 'full': full, 'coronagraph': coronagraph, 'synthesis': synthesis}[name]()

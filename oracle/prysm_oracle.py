@@ -821,6 +821,119 @@ def zernike_nm(n, m, rho, theta):
     return R * math.sqrt(2 * (n + 1) / (2 if m == 0 else 1))
 
 
+# --------------------------------------------------------------------------------------
+# pupil synthesis by recurrence -- the step before the path
+# (prysm/coordinates.py:73-102, 344-378; geometry.py:11-34, 337-372; polynomials/jacobi.py:13-175;
+#  polynomials/_recurrence.py:9-57; polynomials/zernike.py:25-181, 633-690)
+# --------------------------------------------------------------------------------------
+
+
+def make_xy_grid(shape, dx=0, diameter=0, grid=True, dtype=np.float64):
+    """x, y = fftrange(s)*dx per axis, meshgridded.  prysm/coordinates.py:344-378."""
+    if not isinstance(shape, tuple):
+        shape = (shape, shape)
+    if diameter != 0:
+        dx = diameter / max(shape)
+    y, x = (fftrange(s, dtype) * dx for s in shape)
+    if grid:
+        x, y = np.meshgrid(x, y)
+    return x, y
+
+
+def cart_to_polar(x, y):
+    """rho = hypot(x, y), phi = arctan2(y, x).  prysm/coordinates.py:73-102."""
+    return np.hypot(x, y), np.arctan2(y, x)
+
+
+def circle(radius, r):
+    """r - radius <= 0.  prysm/geometry.py:337-372."""
+    return (r - radius) <= 0
+
+
+def antialias(d, dx):
+    """Signed distance -> coverage with a one-sample ramp: clip(0.5 - d/dx, 0, 1).  prysm/geometry.py:11-34."""
+    return np.minimum(np.maximum(0.5 - d / dx, 0), 1)
+
+
+def recurrence_abc(n, alpha, beta):
+    """DLMF 18.9 three-term coefficients, written as the reference writes them.  prysm/polynomials/jacobi.py:13-39."""
+    aplusb = alpha + beta
+    if n == 0 and (aplusb == 0 or aplusb == -1):
+        return 1 / 2 * (alpha + beta) + 1, 1 / 2 * (alpha - beta), 1
+    A = ((2 * n + alpha + beta + 1) * (2 * n + alpha + beta + 2)) / (2 * (n + 1) * (n + alpha + beta + 1))
+    B = ((alpha ** 2 - beta ** 2) * (2 * n + alpha + beta + 1)) / (2 * (n + 1) * (n + alpha + beta + 1) * (2 * n + alpha + beta))
+    C = ((n + alpha) * (n + beta) * (2 * n + alpha + beta + 2)) / ((n + 1) * (n + alpha + beta + 1) * (2 * n + alpha + beta))
+    return A, B, C
+
+
+def jacobi_seq(ns, alpha, beta, x):
+    """P_n^(alpha,beta)(x) for ascending orders ns by P_k = (A x + B) P_{k-1} - C P_{k-2}, coefficients of order
+    k-1; P_0 = 1, P_1 = alpha + 1 + (alpha + beta + 2)(x - 1)/2.  prysm/polynomials/jacobi.py:147-175,
+    _recurrence.py:9-57."""
+    ns = list(ns)
+    out = np.empty((len(ns),) + x.shape, dtype=x.dtype)
+    Pm2 = np.ones_like(x)
+    Pm1 = alpha + 1 + (alpha + beta + 2) * ((x - 1) / 2)
+    want = {n: i for i, n in enumerate(ns)}
+    if 0 in want:
+        out[want[0]] = Pm2
+    if 1 in want:
+        out[want[1]] = Pm1
+    for k in range(2, (ns[-1] if ns else 0) + 1):
+        A, B, C = recurrence_abc(k - 1, alpha, beta)
+        Pn = (A * x + B) * Pm1 - C * Pm2
+        Pm2, Pm1 = Pm1, Pn
+        if k in want:
+            out[want[k]] = Pn
+    return out
+
+
+def jacobi(n, alpha, beta, x):
+    """prysm/polynomials/jacobi.py:42-79."""
+    return jacobi_seq([n], alpha, beta, x)[0]
+
+
+def zernike_norm(n, m):
+    """sqrt(2(n+1)/(1+delta_m0)).  prysm/polynomials/zernike.py:25-27."""
+    return math.sqrt((2 * (n + 1)) / (1 + (1 if m == 0 else 0)))
+
+
+def zernike_nm_seq(nms, r, t, norm=True):
+    """Z_n^m = norm * P_{(n-|m|)/2}^{(0,|m|)}(2r^2 - 1) * r^|m| * {cos(m t) | sin(|m| t)} with the Jacobi sequences
+    shared per |m|.  prysm/polynomials/zernike.py:74-166."""
+    x = 2 * (r * r) - 1
+    nj_max = {}
+    for n, m in nms:
+        am = abs(m)
+        nj_max[am] = max(nj_max.get(am, 0), (n - am) // 2)
+    seqs = {am: jacobi_seq(range(nj + 1), 0, am, x) for am, nj in nj_max.items()}
+    out = np.empty((len(nms),) + r.shape, dtype=r.dtype)
+    for k, (n, m) in enumerate(nms):
+        am = abs(m)
+        jac = seqs[am][(n - am) // 2]
+        if norm:
+            jac = jac * zernike_norm(n, m)
+        if m == 0:
+            out[k] = jac
+        else:
+            out[k] = jac * (np.sin(am * t) if m < 0 else np.cos(am * t)) * r ** am
+    return out
+
+
+def zernike_sum(coefs, nms, x, y, norm=True):
+    """sum_k c_k Z_k on Cartesian coordinates (zero coefficients skipped).  prysm/polynomials/zernike.py:169-181."""
+    nms = tuple(nms)
+    if not nms:
+        return np.zeros_like(x)
+    r, t = cart_to_polar(x, y)
+    Z = zernike_nm_seq(nms, r, t, norm)
+    z = np.zeros_like(x)
+    for c, Zi in zip(coefs, Z):
+        if c != 0.0:
+            z = z + c * Zi
+    return z
+
+
 def synthetic_pupil(N, rdtype=np.float32, seed=20260923, sigma_nm=30.0, diameter=10.0, nmodes=36):
     """SURVEY.md section 8(d) builder: circular aperture of `diameter` mm on an N x N grid
     (dx = diameter/N, prysm/coordinates.py:344-378), OPD = sum of Noll 2..nmodes+1 orthonormal
