@@ -254,6 +254,35 @@ int pb_vortex_phase(pb_handle_t h, int dtype, int charge, const void* xf, const 
 int pb_radial_window(pb_handle_t h, int dtype, int ny, int nx, double fdx, double shift, double a0,
                      double b0, double a1, double b1, void* win, void* xf, void* yf, void* stream);
 
+
+/* ---- pupil synthesis: the step before the path ------------------------
+ * x[iy,ix] = (ix - nx/2)*dx, y[iy,ix] = (iy - ny/2)*dx (make_xy_grid, prysm/coordinates.py:344-378) and their polar
+ * form r = hypot(x, y), t = atan2(y, x) (cart_to_polar, coordinates.py:73-102), real arrays, any of them NULL. */
+int pb_xy_grid(pb_handle_t h, int dtype, int ny, int nx, double dx, void* x, void* y, void* r, void* t,
+               void* stream);
+int pb_cart_to_polar(pb_handle_t h, int dtype, const void* x, const void* y, long long count, void* r,
+                     void* t, void* stream);
+/* aa_dx <= 0: out (uint8) = (r - radius <= 0): geometry.circle (prysm/geometry.py:337-372);
+ * aa_dx  > 0: out (real)  = clip(0.5 - (r - radius)/aa_dx, 0, 1): antialias(circle_sdf(radius, r), aa_dx)
+ *             (prysm/geometry.py:11-34), the grey-edge aperture coronagraph models need. */
+int pb_circle(pb_handle_t h, int dtype, const void* r, long long count, double radius, double aa_dx,
+              void* out, void* stream);
+/* Jacobi polynomials P_j^(alpha,beta)(x), j = 0..nmax, by the three-term recurrence of
+ * prysm/polynomials/jacobi.py:13-39, 147-175; order j is written to out[slots_host[j]] (a (n_out, count) real
+ * array) when slots_host[j] >= 0.  nmax <= 120. */
+int pb_jacobi_seq(pb_handle_t h, int dtype, const void* x, long long count, int nmax, double alpha,
+                  double beta, const int* slots_host, void* out, void* stream);
+/* Zernike polynomials Z_n^m = norm * P_{(n-|m|)/2}^{(0,|m|)}(2r^2-1) * r^|m| * {cos(m t), sin(|m| t)} for k HOST
+ * (n, m) pairs, the Jacobi recurrences shared per |m| (zernike_nm_seq, prysm/polynomials/zernike.py:74-166).
+ * polar != 0: a = r, b = t; polar == 0: a = x, b = y (Cartesian; zernike_sum's input form).
+ * pb_zernike_seq writes the basis out (k, count); pb_zernike_sum writes out (count) = sum_k coefs[k]*Z_k without
+ * materialising the basis (zernike_sum, zernike.py:169-181; zero weights are skipped there too). */
+int pb_zernike_seq(pb_handle_t h, int dtype, int polar, const void* a, const void* b, long long count,
+                   int k, const int* n_host, const int* m_host, int norm, void* out, void* stream);
+int pb_zernike_sum(pb_handle_t h, int dtype, int polar, const void* a, const void* b, long long count,
+                   int k, const int* n_host, const int* m_host, const double* coefs_host, int norm,
+                   void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,12 @@ SIGNATURES = {
     'pb_otf_adjoint_seed': (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     'pb_encircled_energy_adjoint_seed': (_i, [_vp, _i, _i, _i, _d, C.POINTER(_d), C.POINTER(_d), _i, _vp, _vp]),
     'pb_vortex_phase': (_i, [_vp, _i, _i, _vp, _vp, _ll, _vp, _vp]),
+    'pb_xy_grid': (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp]),
+    'pb_cart_to_polar': (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp, _vp]),
+    'pb_circle': (_i, [_vp, _i, _vp, _ll, _d, _d, _vp, _vp]),
+    'pb_jacobi_seq': (_i, [_vp, _i, _vp, _ll, _i, _d, _d, C.POINTER(_i), _vp, _vp]),
+    'pb_zernike_seq': (_i, [_vp, _i, _i, _vp, _vp, _ll, _i, C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp]),
+    'pb_zernike_sum': (_i, [_vp, _i, _i, _vp, _vp, _ll, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_d), _i, _vp, _vp]),
     'pb_radial_window': (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp, _vp]),
 }
 

@@ -505,6 +505,85 @@ def radial_window(shape, fdx, shift, here, nxt, rdtype, dev):
     return win, xf, yf
 
 
+def _iarr(v):
+    v = np.ascontiguousarray(v, dtype=np.int32)
+    return v, v.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def xy_grid(shape, dx, rdtype, dev, want='xy'):
+    """Any of x, y, r, t of make_xy_grid / cart_to_polar from one kernel (pb_xy_grid); returns a dict."""
+    ny, nx = shape
+    out = {k: torch.empty((ny, nx), dtype=rdtype, device=dev) for k in want}
+    any_t = next(iter(out.values()))
+    h, st = _ctx(any_t)
+    h.check(lib.pb_xy_grid(h.ptr, _CODE[rdtype], ny, nx, float(dx), _p(out.get('x')), _p(out.get('y')), _p(out.get('r')),
+                           _p(out.get('t')), st))
+    return out
+
+
+def cart_to_polar(x, y):
+    x = x.contiguous()
+    y = y.to(x.dtype).contiguous()
+    r, t = torch.empty_like(x), torch.empty_like(x)
+    h, st = _ctx(x)
+    h.check(lib.pb_cart_to_polar(h.ptr, _CODE[x.dtype], _p(x), _p(y), x.numel(), _p(r), _p(t), st))
+    return r, t
+
+
+def circle(r, radius, aa_dx=0.0):
+    """bool mask r - radius <= 0, or with aa_dx > 0 the one-sample grey-edge coverage (pb_circle)."""
+    r = r.contiguous()
+    out = torch.empty(r.shape, dtype=r.dtype if aa_dx > 0 else torch.bool, device=r.device)
+    h, st = _ctx(r)
+    h.check(lib.pb_circle(h.ptr, _CODE[r.dtype], _p(r), r.numel(), float(radius), float(aa_dx), _p(out), st))
+    return out
+
+
+def jacobi_seq(ns, alpha, beta, x):
+    x = x.contiguous()
+    ns = [int(n) for n in ns]
+    nmax = max(ns) if ns else 0
+    slots = np.full(nmax + 1, -1, dtype=np.int32)
+    for i, n in enumerate(ns):
+        slots[n] = i
+    _, sp = _iarr(slots)
+    out = torch.empty((len(ns),) + tuple(x.shape), dtype=x.dtype, device=x.device)
+    if not ns:
+        return out
+    h, st = _ctx(x)
+    h.check(lib.pb_jacobi_seq(h.ptr, _CODE[x.dtype], _p(x), x.numel(), nmax, float(alpha), float(beta), sp, _p(out), st))
+    return out
+
+
+def zernike_seq(nms, a, b, norm, polar):
+    a = a.contiguous()
+    b = b.to(a.dtype).contiguous()
+    k = len(nms)
+    out = torch.empty((k,) + tuple(a.shape), dtype=a.dtype, device=a.device)
+    if k == 0:
+        return out
+    n, nptr = _iarr([nm[0] for nm in nms])
+    m, mptr = _iarr([nm[1] for nm in nms])
+    h, st = _ctx(a)
+    h.check(lib.pb_zernike_seq(h.ptr, _CODE[a.dtype], int(polar), _p(a), _p(b), a.numel(), k, nptr, mptr, int(bool(norm)),
+                               _p(out), st))
+    return out
+
+
+def zernike_sum(coefs, nms, a, b, norm, polar):
+    a = a.contiguous()
+    b = b.to(a.dtype).contiguous()
+    k = len(nms)
+    out = torch.empty(a.shape, dtype=a.dtype, device=a.device)
+    n, nptr = _iarr([nm[0] for nm in nms])
+    m, mptr = _iarr([nm[1] for nm in nms])
+    c, cptr = _darr(np.asarray(coefs, dtype=np.float64)[:k])
+    h, st = _ctx(a)
+    h.check(lib.pb_zernike_sum(h.ptr, _CODE[a.dtype], int(polar), _p(a), _p(b), a.numel(), k, nptr, mptr, cptr,
+                               int(bool(norm)), _p(out), st))
+    return out
+
+
 def launch_count(dev=None):
     dev = device() if dev is None else torch.device(dev)
     return capi.launch_count(dev.index)
