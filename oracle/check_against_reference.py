@@ -227,6 +227,30 @@ for prec, rdt, cdt, eps in ((64, np.float64, np.complex128, 1e-13), (32, np.floa
     cz[3] = 0
     check(tag + 'zernike_sum', O.zernike_sum(cz, nms, xo, yo), pz_sum(cz, nms, xr, yr), eps * 10)
 
+    # ---- image-chain consumers (rank 4)
+    from prysm import convolution as pconv
+    ob = rng.random((12, 10)).astype(rdt)
+    ps = rng.random((12, 10)).astype(rdt)
+    obc = crand(rng, (12, 10), cdt)
+    check(tag + 'conv real', O.conv(ob, ps), pconv.conv(ob, ps), eps)
+    check(tag + 'conv complex object', O.conv(obc, ps), pconv.conv(obc, ps), eps)
+    tf1 = rng.random((12, 10)).astype(rdt)
+    tf2 = crand(rng, (12, 10), cdt)
+    for sh in (False, True):
+        check(tag + f'apply_transfer_functions arrays shift={sh}', O.apply_transfer_functions(ob, [tf1, tf2], sh),
+              pconv.apply_transfer_functions(ob, 0.5, [tf1, tf2], shift=sh), eps)
+        seen = {}
+
+        def probe(fx, fy, fr, ft):
+            seen.update(fx=fx, fy=fy, fr=fr, ft=ft)
+            return np.ones(ob.shape, dtype=rdt)
+        pconv.apply_transfer_functions(ob, 0.5, [probe], shift=sh)
+        for nm, v in zip(('fx', 'fy', 'fr', 'ft'), O.transfer_function_grids(ob.shape, 0.5, sh, rdt)):
+            check(tag + f'tf grid {nm} shift={sh}', v, seen[nm], eps)
+    for zoom in (0.5, 2, (2, 1.5)):
+        check(tag + f'fourier_resample zoom={zoom}', O.fourier_resample(ob, zoom, rdt), fttools.fourier_resample(ob, zoom), eps * 2)
+    check(tag + 'fourier_resample complex', O.fourier_resample(obc, 2, rdt), fttools.fourier_resample(obc, 2), eps * 2)
+
 # pupil builder (fp64 maths, cast at the end)
 for j in range(1, 60):
     assert O.noll_to_nm(j) == noll_to_nm(j), j

@@ -266,8 +266,43 @@ def synthesis():
     print(f'synthesis.npz written, {len(g)} arrays')
 
 
+def imagechain():
+    """Image-chain consumers of the path's FFTs -> imagechain.npz."""
+    from prysm import convolution
+    rng = np.random.default_rng(20260926)
+    g = {}
+    ob = rng.random((36, 30))
+    ps = rng.random((36, 30))
+    obc = crand(rng, (36, 30))
+    odd = rng.random((15, 9))
+    g.update(obj=ob, psf=ps, obj_c=obc, odd_obj=odd, odd_psf=rng.random((15, 9)))
+    g['conv_real'] = convolution.conv(ob, ps)
+    g['conv_cplx'] = convolution.conv(obc, ps)
+    g['conv_odd'] = convolution.conv(odd, g['odd_psf'])
+    tf1 = rng.random((36, 30))
+    tf2 = crand(rng, (36, 30))
+    g.update(tf1=tf1, tf2=tf2)
+    for sh in (False, True):
+        g[f'atf_shift{int(sh)}'] = convolution.apply_transfer_functions(ob, 0.5, [tf1, tf2], shift=sh)
+        g[f'atf_c_shift{int(sh)}'] = convolution.apply_transfer_functions(obc, 0.5, [tf1], shift=sh)
+        seen = {}
+
+        def probe(fx, fy, fr, ft):
+            seen.update(fx=fx, fy=fy, fr=fr, ft=ft)
+            return np.exp(-(fr / 0.7) ** 2)                     # a Gaussian MTF
+        g[f'atf_callable_shift{int(sh)}'] = convolution.apply_transfer_functions(ob, 0.5, [probe], shift=sh)
+        for k, v in seen.items():
+            g[f'grid_{k}_shift{int(sh)}'] = v
+    for i, zoom in enumerate((0.5, 2, (2, 1.5))):
+        g[f'resample{i}'] = fttools.fourier_resample(ob, zoom)
+    g['resample_c'] = fttools.fourier_resample(obc, 2)
+    np.savez_compressed(os.path.join(OUT, 'imagechain.npz'), **g)
+    print(f'imagechain.npz written, {len(g)} arrays')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['small', 'full', 'coronagraph', 'synthesis']   # name the fixtures to (re)write
+    which = sys.argv[1:] or ['small', 'full', 'coronagraph', 'synthesis', 'imagechain']   # name the fixtures to (re)write
     for name in which:
-        {'small': small, 'full': full, 'coronagraph': coronagraph, 'synthesis': synthesis}[name]()
+        {'small': small, 'full': full, 'coronagraph': coronagraph, 'synthesis': synthesis,
+         'imagechain': imagechain}[name]()

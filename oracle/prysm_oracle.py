@@ -822,6 +822,64 @@ def zernike_nm(n, m, rho, theta):
 
 
 # --------------------------------------------------------------------------------------
+# image-chain consumers of the same FFTs  (prysm/convolution.py:9-114, fttools.py:538-593)
+# --------------------------------------------------------------------------------------
+
+
+def conv(obj, psf):
+    """fftshift(ifft2(fft2(ifftshift(o)) * fft2(ifftshift(h)))), real part for a real object.  prysm/convolution.py:9-32."""
+    O = sfft.fft2(sfft.ifftshift(obj))
+    H = sfft.fft2(sfft.ifftshift(psf))
+    i = sfft.fftshift(sfft.ifft2(O * H))
+    return i.real if not np.iscomplexobj(obj) else i
+
+
+def forward_ft_unit(dx, samples, shift=True, dtype=np.float64):
+    """fftfreq(samples, dx), fftshifted on request.  prysm/fttools.py:128-152."""
+    u = fftfreq(samples, dx, dtype)
+    return sfft.fftshift(u) if shift else u
+
+
+def transfer_function_grids(shape, dx, shift=False, dtype=np.float64):
+    """fx (1, N), fy (M, 1), fr, ft handed to callable transfer functions.  prysm/convolution.py:73-85."""
+    uy, ux = (forward_ft_unit(dx, n, shift, dtype) for n in shape)
+    fx, fy = ux.reshape(1, -1), uy.reshape(-1, 1)
+    return fx, fy, np.hypot(fx, fy), np.arctan2(fy, fx)
+
+
+def apply_transfer_functions(obj, tfs, shift=False):
+    """Object spectrum times each transfer-function ARRAY, back to the image.  prysm/convolution.py:35-114 (callables are
+    evaluated by the caller on transfer_function_grids)."""
+    O = sfft.fft2(sfft.ifftshift(obj))
+    if shift:
+        O = sfft.fftshift(O)
+    for tf in tfs:
+        O = O * tf
+    i = sfft.fftshift(sfft.ifft2(sfft.ifftshift(O) if shift else O))
+    return i.real if not np.iscomplexobj(obj) else i
+
+
+def fourier_resample(f, zoom, rdtype=np.float64):
+    """Centered FFT, then a sign=+1 matrix DFT onto M = int(m*zoom) samples spaced 1/zoom, / (m n).
+    prysm/fttools.py:538-593."""
+    if zoom == 1:
+        return f
+    zoom = (zoom, zoom) if isinstance(zoom, (float, int)) else tuple(float(z) for z in zoom)
+    if len(zoom) != 2 or any(z <= 0 for z in zoom):
+        raise ValueError('zoom must contain two positive values')
+    m, n = f.shape
+    M, N = int(m * zoom[0]), int(n * zoom[1])
+    if M < 1 or N < 1:
+        raise ValueError('zoom produces an empty output')
+    F = sfft.fftshift(sfft.fft2(sfft.ifftshift(f)))
+    x, y = fftrange(n, rdtype), fftrange(m, rdtype)
+    fx = fftrange(N, rdtype) * (1.0 / zoom[1] / n)
+    fy = fftrange(M, rdtype) * (1.0 / zoom[0] / m)
+    out = MDFT(x, y, fx, fy, +1)(F) * (1 / (m * n))
+    return out if np.iscomplexobj(f) else out.real
+
+
+# --------------------------------------------------------------------------------------
 # pupil synthesis by recurrence -- the step before the path (SURVEY.md 8(f) rank 3)
 # (prysm/coordinates.py:73-102, 344-378; geometry.py:11-34, 337-372; polynomials/jacobi.py:13-175;
 #  polynomials/_recurrence.py:9-57; polynomials/zernike.py:25-181, 633-690)
