@@ -283,6 +283,22 @@ int pb_zernike_sum(pb_handle_t h, int dtype, int polar, const void* a, const voi
                    int k, const int* n_host, const int* m_host, const double* coefs_host, int norm,
                    void* out, void* stream);
 
+
+/* ---- image-chain consumers of the same FFTs ------------------------------
+ * conv(obj, psf) of two REAL arrays (prysm/convolution.py:9-32) as one forward and one inverse transform:
+ * pb_balance_scale: *s_dev (a DEVICE double) = sqrt(sum a^2 / sum b^2) (1 if either sum is 0 / not finite): the two
+ *   arrays share one transform whose rounding error is relative to the larger of them, so the PSF is scaled to the
+ *   object's norm for the round trip -- on the device, no host synchronisation;
+ * pb_pack_complex: out = re + i*s*im (im NULL -> 0; im_scale_dev NULL -> s = 1); pb_fft2 of that gives Z = O + i*s*H;
+ * pb_packed_spectrum_product: out[k] = scale/s * (Z[k]^2 - conj(Z[-k])^2)/(4i) = scale * O[k]*H[k], indices modulo
+ *   (ny, nx), unshifted spectrum order; out must not alias Z. */
+int pb_balance_scale(pb_handle_t h, int dtype, const void* a, const void* b, long long count, double* s_dev,
+                     void* stream);
+int pb_pack_complex(pb_handle_t h, int dtype, const void* re, const void* im, const double* im_scale_dev,
+                    long long count, void* out, void* stream);
+int pb_packed_spectrum_product(pb_handle_t h, int dtype, const void* Z, int ny, int nx, double scale,
+                               const double* im_scale_dev, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

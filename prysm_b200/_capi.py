@@ -64,6 +64,9 @@ SIGNATURES = {
     'pb_jacobi_seq': (_i, [_vp, _i, _vp, _ll, _i, _d, _d, C.POINTER(_i), _vp, _vp]),
     'pb_zernike_seq': (_i, [_vp, _i, _i, _vp, _vp, _ll, _i, C.POINTER(_i), C.POINTER(_i), _i, _vp, _vp]),
     'pb_zernike_sum': (_i, [_vp, _i, _i, _vp, _vp, _ll, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_d), _i, _vp, _vp]),
+    'pb_balance_scale': (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp]),
+    'pb_pack_complex': (_i, [_vp, _i, _vp, _vp, _vp, _ll, _vp, _vp]),
+    'pb_packed_spectrum_product': (_i, [_vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
     'pb_radial_window': (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp, _vp]),
 }
 

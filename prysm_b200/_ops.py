@@ -584,6 +584,37 @@ def zernike_sum(coefs, nms, a, b, norm, polar):
     return out
 
 
+def balance_scale(a, b):
+    """Device scalar s = sqrt(sum a^2 / sum b^2) (pb_balance_scale); stays on the device."""
+    a = a.contiguous()
+    b = b.to(a.dtype).contiguous()
+    s = torch.empty(1, dtype=torch.float64, device=a.device)
+    h, st = _ctx(a)
+    h.check(lib.pb_balance_scale(h.ptr, _CODE[a.dtype], _p(a), _p(b), a.numel(), _p(s), st))
+    return s
+
+
+def pack_complex(re, im=None, im_scale=None):
+    re = re.contiguous()
+    if re.dtype not in _CPLX_OF:
+        re = re.to(torch.float32)
+    im = None if im is None else im.to(re.dtype).contiguous()
+    out = torch.empty(re.shape, dtype=_CPLX_OF[re.dtype], device=re.device)
+    h, st = _ctx(re)
+    h.check(lib.pb_pack_complex(h.ptr, _CODE[re.dtype], _p(re), _p(im), _p(im_scale), re.numel(), _p(out), st))
+    return out
+
+
+def packed_spectrum_product(Z, scale=1.0, im_scale=None):
+    """O*H from Z = FFT2(o + i*s*h) of two real arrays (pb_packed_spectrum_product)."""
+    Z = Z.contiguous()
+    ny, nx = Z.shape
+    out = torch.empty_like(Z)
+    h, st = _ctx(Z)
+    h.check(lib.pb_packed_spectrum_product(h.ptr, _CODE[Z.dtype], _p(Z), ny, nx, float(scale), _p(im_scale), _p(out), st))
+    return out
+
+
 def launch_count(dev=None):
     dev = device() if dev is None else torch.device(dev)
     return capi.launch_count(dev.index)

@@ -12,6 +12,7 @@ prysm/propagation/wavefront.py:11-25, so those module globals are re-bound as we
 """
 import importlib
 
+from . import convolution as _conv
 from . import fttools as _ft
 from . import otf as _otf
 from . import polynomials as _poly
@@ -44,7 +45,8 @@ _TARGETS = {
                           'prepare_multiresolution': _prop.prepare_multiresolution,
                           'MultiResolutionExecutor': _prop.MultiResolutionExecutor},
     'prysm.fttools': {'MDFT': _ft.MDFT, 'CZT': _ft.CZT, 'FFTDFT': _ft.FFTDFT, 'pad2d': _ft.pad2d,
-                      'crop_center': _ft.crop_center},
+                      'crop_center': _ft.crop_center, 'fourier_resample': _ft.fourier_resample},
+    'prysm.convolution': {'conv': _conv.conv, 'apply_transfer_functions': _conv.apply_transfer_functions},
     'prysm.otf': {n: getattr(_otf, n) for n in (
         'transform_psf', 'transform_psf_adjoint', 'mtf_from_psf', 'ptf_from_psf', 'otf_from_psf', 'mtf_ptf_otf_from_psf',
         'mtf_from_psf_adjoint', 'ptf_from_psf_adjoint', 'otf_from_psf_adjoint', 'encircled_energy',
