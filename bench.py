@@ -6,8 +6,8 @@
 
 Workload (BASELINE configs[1], SURVEY.md 8d "C2"): one unit = `Wavefront.focus(efl, Q=2)` of a
 2048^2 complex64 Zernike-aberrated pupil -> 4096^2 complex64 field.  One step = one pass over a
-batch of BATCH distinct pupils resident in HBM (BATCH*32 MiB of inputs >> 126 MB L2, outputs into
-a ring of 4096^2 buffers), so no step can be served from cache.  Multi-GPU = independent replicas
+batch of BATCH distinct pupils resident in HBM through ONE batched library call (BATCH*32 MiB of
+inputs and BATCH*128 MiB of distinct outputs >> 126 MB L2), so no step can be served from cache.  Multi-GPU = independent replicas
 with disjoint batches (weak scaling, no collective on the data path).
 
 The JSON line carries: value (device-resident throughput, CUDA events, max over ranks), e2e (same
@@ -32,7 +32,6 @@ K = N * Q
 HENE = 0.6328
 EFL = 100.0
 BATCH = 16                       # pupils per step (16 x 32 MiB = 512 MiB of distinct inputs)
-OUT_RING = 4                     # 4 x 128 MiB output buffers
 ALG_BYTES = 8 * N * N + 8 * K * K  # read pupil + write field = 167 772 160 B / propagation
 METRIC = '2048x2048 pupil->PSF propagations/sec'
 
@@ -229,13 +228,14 @@ def run_b200(args):
     for i in range(BATCH):  # distinct unit-modulus piston per pupil (built once, outside timing)
         ph = torch.rand((), generator=gen, device=dev) * 6.2831853
         pupils.append((base[i % 2] * torch.polar(torch.ones((), device=dev), ph)).contiguous())
-    outs = [torch.empty((K, K), dtype=torch.complex64, device=dev) for _ in range(OUT_RING)]
+    stack = torch.stack(pupils)                                   # (BATCH, N, N): 512 MiB of distinct inputs
+    del pupils
+    out = torch.empty((BATCH, K, K), dtype=torch.complex64, device=dev)   # 2 GiB of distinct outputs
     scale = 1.0 / K
     torch.cuda.synchronize()
 
-    def step():
-        for i in range(BATCH):
-            _ops.fft2(pupils[i], (K, K), dir=-1, scale=scale, shift_in=True, shift_out=True, out=outs[i % OUT_RING])
+    def step():  # one batched library call (pb_fft2_batch): the fields of a step share launches, 8 per launch pair
+        _ops.fft2_batch(stack, (K, K), dir=-1, scale=scale, shift_in=True, shift_out=True, out=out)
 
     def barrier():
         if world > 1:
@@ -317,12 +317,14 @@ def run_b200(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'complex64', 'data': 'synthetic',
             'config': {'workload': 'C2: 2048x2048 complex64 pupil -> Wavefront.focus(Q=2) -> 4096x4096 field',
                        'propagations_per_step': BATCH, 'parallelism': f'replicas x{world}',
-                       'l2_policy': f'{BATCH} distinct 32 MiB inputs + {OUT_RING} x 128 MiB output ring per step (>> 126 MB L2)'},
+                       'l2_policy': f'{BATCH} distinct 32 MiB inputs + {BATCH} distinct 128 MiB outputs per step (>> 126 MB L2)',
+                       'call': 'one pb_fft2_batch per step (propagation.focus on a (16, 2048, 2048) stack)'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         # dram__bytes_read + dram__bytes_write of the two kernels of one propagation from the
-                         # committed `ncu --set full` captures (profiles/r01_ncu_full_summary.txt; cold cache, so the
-                         # 64 MiB intermediate is re-read from DRAM there; back to back it is served from L2)
-                         'traffic': 33631232 + 19407616 + 67170304 + 75995904, 'peak_source': peak_src,
+                         # (dram__bytes_read + dram__bytes_write) / 8 fields of the two kernels of one launch pair from the
+                         # committed `ncu --set full` capture of this command (profiles/r01_ncu_focus_batched_summary.txt):
+                         # 33.6 + 60.8 (column kernel) + 67.1 + 126.9 (row kernel) MB -- with 8 fields per launch pair
+                         # the 64 MiB intermediates spill to HBM once each way
+                         'traffic': (268553216 + 486104000 + 536974336 + 1014972000) // 8, 'peak_source': peak_src,
                          'algorithmic_bytes_per_propagation': ALG_BYTES,
                          'kernel': 'fused focus pipeline (all passes of one propagation), per GPU',
                          'us_per_propagation': t_prop * 1e6},

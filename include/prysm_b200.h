@@ -83,6 +83,16 @@ int pb_fft2(pb_handle_t h, int dtype,
             int ky, int kx, int dir, double scale, int shift_in, int shift_out,
             void* out, int out_kind, double weight, int oy, int ox, long long out_ld,
             void* stream);
+/* pb_fft2 over `batch` independent fields in one call: field b starts at in + b*in_bs, amp + b*amp_bs (0 = one
+ * amplitude shared by all) and out + b*out_bs, strides in elements of the respective array's scalar type.  On the
+ * fused focus shapes the fields share launches (two per launch pair by default), which evens out the 3.46-wave
+ * column pass and the 9.2-round row pass of a single 2048^2 field; other shapes run field by field.  The reference
+ * has no batch form: fft.py:7-25 is called once per wavefront. */
+int pb_fft2_batch(pb_handle_t h, int dtype, const void* in, int in_kind, const void* amp, int amp_kind,
+                  double kscale, int batch, long long in_bs, long long amp_bs, int ny, int nx,
+                  long long in_ld, int ky, int kx, int dir, double scale, int shift_in, int shift_out,
+                  void* out, int out_kind, double weight, int oy, int ox, long long out_ld,
+                  long long out_bs, void* stream);
 
 /* ---- 1-D FFT along one axis of a 2-D array, numpy fft(a, n, axis) semantics ------------
  * Zero-extends or truncates to n along `axis` (0 = y/columns, 1 = x/rows).

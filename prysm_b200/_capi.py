@@ -28,6 +28,8 @@ SIGNATURES = {
     'pb_launch_count': (_ll, [_vp]),
     'pb_fft2': (_i, [_vp, _i, _vp, _i, _vp, _i, _d, _i, _i, _ll, _i, _i, _i, _d, _i, _i,
                      _vp, _i, _d, _i, _i, _ll, _vp]),
+    'pb_fft2_batch': (_i, [_vp, _i, _vp, _i, _vp, _i, _d, _i, _ll, _ll, _i, _i, _ll, _i, _i, _i, _d, _i, _i,
+                           _vp, _i, _d, _i, _i, _ll, _ll, _vp]),
     'pb_fft1': (_i, [_vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _d, _vp, _ll, _vp]),
     'pb_axis_dft': (_i, [_vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _d, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _ll, _vp]),
     'pb_czt_plan': (_i, [_vp, _i, _i, _i, _i, _d, _d, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),

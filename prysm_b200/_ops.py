@@ -120,6 +120,41 @@ def fft2(field, k=None, *, dir=-1, scale=1.0, shift_in=False, shift_out=False, c
     return out
 
 
+def fft2_batch(fields, k=None, *, dir=-1, scale=1.0, shift_in=False, shift_out=False, out_kind=capi.OUT_COMPLEX, out=None,
+               amp=None, opd=None, kscale=0.0):
+    """pb_fft2_batch over a (B, ny, nx) stack -> (B, ky, kx): either `fields` (complex or real) or `opd` (B, ny, nx)
+    with an optional amplitude that is (ny, nx) (shared) or (B, ny, nx)."""
+    amp_kind, amp_t, amp_bs = capi.AMP_NONE, None, 0
+    if opd is not None:
+        src = opd if opd.dtype in _CPLX_OF else opd.to(torch.float32)
+        in_kind, cdtype = capi.IN_AMP_OPD, _CPLX_OF[src.dtype]
+        if amp is not None:
+            if amp.dtype in (torch.bool, torch.uint8):
+                amp_kind, amp_t = capi.AMP_U8, amp.contiguous()
+            else:
+                amp_kind, amp_t = capi.AMP_REAL, amp.to(src.dtype).contiguous()
+            amp_bs = amp_t.stride(0) if amp_t.ndim == 3 else 0
+    else:
+        src = fields
+        if src.is_complex():
+            in_kind, cdtype = capi.IN_COMPLEX, src.dtype
+        else:
+            if src.dtype not in _CPLX_OF:
+                src = src.to(torch.float32)
+            in_kind, cdtype = capi.IN_REAL, _CPLX_OF[src.dtype]
+    src = src.contiguous()
+    nb, ny, nx = src.shape
+    ky, kx = (ny, nx) if k is None else k
+    if out is None:
+        odt = cdtype if out_kind == capi.OUT_COMPLEX else _REAL_OF[cdtype]
+        out = torch.empty((nb, ky, kx), dtype=odt, device=src.device)
+    h, st = _ctx(src)
+    h.check(lib.pb_fft2_batch(h.ptr, _CODE[cdtype], _p(src), in_kind, _p(amp_t), amp_kind, float(kscale), nb,
+                              src.stride(0), amp_bs, ny, nx, src.stride(1), ky, kx, int(dir), float(scale), int(shift_in),
+                              int(shift_out), _p(out), out_kind, 1.0, ky, kx, out.stride(1), out.stride(0), st))
+    return out
+
+
 def fft1(a, n=None, axis=-1, dir=-1, scale=1.0):
     """pb_fft1: numpy fft(a, n, axis) on a 2-D complex tensor."""
     a = ascomplex(a).contiguous()

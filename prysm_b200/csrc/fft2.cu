@@ -206,6 +206,42 @@ extern "C" int pb_fft2(pb_handle_t hh, int dtype, const void* in, int in_kind, c
     return fft2_generic(h, a, st);
 }
 
+extern "C" int pb_fft2_batch(pb_handle_t hh, int dtype, const void* in, int in_kind, const void* amp, int amp_kind,
+                             double kscale, int batch, long long in_bs, long long amp_bs, int ny, int nx, long long in_ld,
+                             int ky, int kx, int dir, double scale, int shift_in, int shift_out, void* out, int out_kind,
+                             double weight, int oy, int ox, long long out_ld, long long out_bs, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h) return PB_ERR_INVALID;
+    if (batch < 1) return fail(h, PB_ERR_INVALID, "batch must be >= 1");
+    if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
+    if (ny < 1 || nx < 1 || ky < ny || kx < nx) return fail(h, PB_ERR_INVALID, "need 1 <= n <= k on both axes");
+    if (oy < 1 || ox < 1 || oy > ky || ox > kx) return fail(h, PB_ERR_INVALID, "crop window must fit the transform");
+    if (dir != -1 && dir != 1) return fail(h, PB_ERR_INVALID, "dir must be -1 or +1");
+    if (!in || !out) return fail(h, PB_ERR_INVALID, "null array pointer");
+    if (in_kind < 0 || in_kind > 2 || out_kind < 0 || out_kind > 2) return fail(h, PB_ERR_INVALID, "bad in/out kind");
+    if (in_ld < nx || out_ld < ox) return fail(h, PB_ERR_INVALID, "row pitch smaller than the row");
+    if (batch > 1 && (in_bs < (long long)(ny - 1) * in_ld + nx || out_bs < (long long)(oy - 1) * out_ld + ox))
+        return fail(h, PB_ERR_INVALID, "batch stride smaller than one field");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = try_tuned_fft2_batch(h, dtype, in, in_kind, amp, amp_kind, kscale / (2.0 * M_PI), batch, in_bs, amp_bs, ny, nx,
+                                  in_ld, ky, kx, dir, scale, shift_in, shift_out, out, out_kind, weight, oy, ox, out_ld,
+                                  out_bs, st);
+    if (rc != PB_ERR_UNSUPPORTED) return rc;
+    // shapes outside the fused kernels: one field at a time through the generic passes
+    const size_t rsz = dtype == PB_C64 ? 4 : 8;
+    const size_t in_elt = in_kind == PB_IN_COMPLEX ? 2 * rsz : rsz;
+    const size_t amp_elt = amp_kind == PB_AMP_U8 ? 1 : rsz;
+    const size_t out_elt = out_kind == PB_OUT_COMPLEX ? 2 * rsz : rsz;
+    for (int b = 0; b < batch; ++b) {
+        Fft2Args a{dtype, reinterpret_cast<const char*>(in) + (size_t)b * in_bs * in_elt, in_kind,
+                   amp ? reinterpret_cast<const char*>(amp) + (size_t)b * amp_bs * amp_elt : nullptr, amp_kind,
+                   kscale / (2.0 * M_PI), ny, nx, in_ld, ky, kx, dir, scale, shift_in, shift_out,
+                   reinterpret_cast<char*>(out) + (size_t)b * out_bs * out_elt, out_kind, weight, oy, ox, out_ld};
+        PB_TRY(fft2_generic(h, a, st));
+    }
+    return PB_OK;
+}
+
 extern "C" int pb_fft1(pb_handle_t hh, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int n,
                        int dir, double scale, void* out, long long out_ld, void* stream) {
     Handle* h = reinterpret_cast<Handle*>(hh);

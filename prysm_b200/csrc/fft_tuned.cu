@@ -268,7 +268,10 @@ struct FocusParams {
     const float4* plan;     // Geo<N> plan table
     // row kernel output
     void* out; long long out_ld; int out_kind; float scale; float weight;
-    int nrows;              // row kernel: 2N
+    int nrows;              // row kernel: batch * 2N
+    // batch of independent fields in one launch pair (blockIdx.y in the column kernel; rows of all fields in the row
+    // kernel's persistent loop): element strides of in / amp / out in units of their own scalar type
+    long long in_bs, amp_bs, out_bs;
 };
 
 // ---- column pass: both half-transforms down T adjacent columns -------------------------------------
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(T * L / 16) focus_col_kernel(const FocusParams
     uint64_t* bar = reinterpret_cast<uint64_t*>(plan_s + G::PLAN);
     const int c = threadIdx.x % T, t = threadIdx.x / T;
     const int col = blockIdx.x * T + c;
+    const long long fb = blockIdx.y;                                   // field of the batch
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -290,18 +294,19 @@ __global__ void __launch_bounds__(T * L / 16) focus_col_kernel(const FocusParams
     P2 v[16];
     float2 x[16];
     if (p.in_kind == PB_IN_COMPLEX) {
-        const float2* __restrict__ src = reinterpret_cast<const float2*>(p.in) + col + (long long)t * p.in_ld;
+        const float2* __restrict__ src = reinterpret_cast<const float2*>(p.in) + fb * p.in_bs + col + (long long)t * p.in_ld;
         const long long step = (long long)G::NT * p.in_ld;
 #pragma unroll
         for (int n = 0; n < 16; ++n) x[n] = ld_stream(src + n * step);
     } else {
-        const float* __restrict__ opd = reinterpret_cast<const float*>(p.in) + col;
+        const float* __restrict__ opd = reinterpret_cast<const float*>(p.in) + fb * p.in_bs + col;
+        const long long ab = fb * p.amp_bs + col;
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
             const long long off = (long long)(n * G::NT + t) * p.in_ld;
             float a = 1.0f;
-            if (p.amp_kind == PB_AMP_REAL) a = __ldg(reinterpret_cast<const float*>(p.amp) + col + off);
-            else if (p.amp_kind == PB_AMP_U8) a = __ldg(reinterpret_cast<const unsigned char*>(p.amp) + col + off) ? 1.0f : 0.0f;
+            if (p.amp_kind == PB_AMP_REAL) a = __ldg(reinterpret_cast<const float*>(p.amp) + ab + off);
+            else if (p.amp_kind == PB_AMP_U8) a = __ldg(reinterpret_cast<const unsigned char*>(p.amp) + ab + off) ? 1.0f : 0.0f;
             float2 e = make_float2(0.f, 0.f);
             if (a != 0.0f) {
                 e = expi_turns(p.kturns * (double)__ldg(opd + off), 0.0f);
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(T * L / 16) focus_col_kernel(const FocusParams
     for (int g = 0; g < G::GI; ++g) dftR<G::R3, INV>(v + g * G::R3);
     // (-dir*i)^k with k = 2j + lane; j = t + g*NT + 256*kk has the parity of t
     const float sgn = (t & 1) ? -1.0f : 1.0f;
-    float2* __restrict__ dA = p.tmp + col + (long long)t * L;
+    float2* __restrict__ dA = p.tmp + fb * (2LL * L * L) + col + (long long)t * L;
     float2* __restrict__ dB = dA + (long long)L * L;
 #pragma unroll
     for (int g = 0; g < G::GI; ++g)
@@ -379,10 +384,11 @@ __global__ void __launch_bounds__(L / 16) focus_row_kernel(const FocusParams p) 
         __syncthreads();  // exchange buffer is free for the next row
 #pragma unroll
         for (int g = 0; g < GI; ++g) dftR<R3, INV>(v + g * R3);
-        const int phs = r / L, rr = r - phs * L;
+        const int fb = r / (2 * L), rf = r - fb * (2 * L);   // field of the batch, row within its [2][L] planes
+        const int phs = rf / L, rr = rf - phs * L;
         const int orow = (2 * rr + phs + L) & (2 * L - 1);  // fftshift along y
         if (p.out_kind == PB_OUT_COMPLEX) {
-            float4* __restrict__ dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(p.out) + (long long)orow * p.out_ld);
+            float4* __restrict__ dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(p.out) + fb * p.out_bs + (long long)orow * p.out_ld);
 #pragma unroll
             for (int g = 0; g < GI; ++g)
 #pragma unroll
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(L / 16) focus_row_kernel(const FocusParams p) 
                     st_stream(dst + ((j + L / 2) & (L - 1)), o);
                 }
         } else {
-            float2* __restrict__ dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + (long long)orow * p.out_ld);
+            float2* __restrict__ dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + fb * p.out_bs + (long long)orow * p.out_ld);
             const float2 s2 = make_float2(p.scale * p.scale, p.scale * p.scale);
             const float2 wgt = make_float2(p.weight, p.weight);
 #pragma unroll
@@ -445,7 +451,7 @@ int get_focus_plan(Handle* h, const float4** out) {
 }
 
 template <int L, bool INV>
-int launch_focus(Handle* h, FocusParams p, cudaStream_t st) {
+int launch_focus(Handle* h, FocusParams p, int batch, cudaStream_t st) {
     using G = Geo<L>;
     constexpr int T = 4;
     const size_t smem_col = (size_t)(T * (G::SBUF + 2) + G::PLAN) * sizeof(float4) + 2 * sizeof(uint64_t);
@@ -472,8 +478,8 @@ int launch_focus(Handle* h, FocusParams p, cudaStream_t st) {
         PB_CUDA(h, cudaFuncSetAttribute(focus_col_kernel<L, INV, T>, cudaFuncAttributePreferredSharedMemoryCarveout, col_pct));
     }
     PB_TRY(get_focus_plan<L>(h, &p.plan));
-    p.nrows = 2 * L;
-    focus_col_kernel<L, INV, T><<<L / T, T * G::NT, smem_col, st>>>(p);
+    p.nrows = batch * 2 * L;
+    focus_col_kernel<L, INV, T><<<dim3(L / T, batch), T * G::NT, smem_col, st>>>(p);
     PB_LAUNCH_CHECK(h);
     focus_row_kernel<L, INV><<<std::min(h->sm_count * row_ctas, p.nrows), L / 16, smem_row, st>>>(p);
     PB_LAUNCH_CHECK(h);
@@ -682,34 +688,59 @@ int try_tuned_axis_pass(Handle* h, const AxisPass& p, cudaStream_t st) {
     }
 }
 
-int try_tuned_fft2(Handle* h, int dtype, const void* in, int in_kind, const void* amp, int amp_kind, double kturns,
-                   int ny, int nx, long long in_ld, int ky, int kx, int dir, double scale, int shift_in, int shift_out,
-                   void* out, int out_kind, double weight, int oy, int ox, long long out_ld, cudaStream_t st) {
+// fields per launch pair: more than one evens out the tails (512 column tiles on 148 SMs = 3.46 waves; 4096 rows on
+// 444 persistent row CTAs = 9.2 rounds).  The intermediates of a group (64 MiB each at N = 2048) no longer fit L2
+// together and spill to HBM, which has the headroom: measured 87.3 / 78.8 / 76.7 / 75.7 us per field at 1 / 2 / 4 / 8.
+static int focus_fields_per_launch() {
+    static const int n = [] { const char* e = getenv("PB_FOCUS_BATCH"); return e ? std::max(1, atoi(e)) : 8; }();
+    return n;
+}
+
+int try_tuned_fft2_batch(Handle* h, int dtype, const void* in, int in_kind, const void* amp, int amp_kind, double kturns,
+                         int batch, long long in_bs, long long amp_bs, int ny, int nx, long long in_ld, int ky, int kx, int dir,
+                         double scale, int shift_in, int shift_out, void* out, int out_kind, double weight, int oy, int ox,
+                         long long out_ld, long long out_bs, cudaStream_t st) {
     static const bool disabled = getenv("PB_DISABLE_TUNED") != nullptr;
     if (disabled) return PB_ERR_UNSUPPORTED;
     if (dtype != PB_C64 || ny != nx || ky != 2 * ny || kx != 2 * nx || !shift_in || !shift_out || oy != ky || ox != kx)
         return PB_ERR_UNSUPPORTED;
     if (nx != 512 && nx != 1024 && nx != 2048) return PB_ERR_UNSUPPORTED;
     if (in_kind == PB_IN_REAL) return PB_ERR_UNSUPPORTED;
-    if (out_kind == PB_OUT_COMPLEX ? (out_ld & 1) || ((uintptr_t)out & 15) : (out_ld & 1) || ((uintptr_t)out & 7))
+    if (out_kind == PB_OUT_COMPLEX ? (out_ld & 1) || (out_bs & 1) || ((uintptr_t)out & 15) : (out_ld & 1) || (out_bs & 1) || ((uintptr_t)out & 7))
         return PB_ERR_UNSUPPORTED;  // vector stores need aligned rows
     const int N = nx;
-    FocusParams p;
-    p.in = in; p.in_kind = in_kind; p.amp = amp; p.amp_kind = amp_kind; p.kturns = kturns; p.in_ld = in_ld;
+    const int per = std::min(batch, focus_fields_per_launch());
     void* tmp = nullptr;
-    PB_TRY(ensure_scratch(h, 0, (size_t)2 * N * N * sizeof(float2), &tmp));
-    p.tmp = reinterpret_cast<float2*>(tmp);
-    p.plan = nullptr;
-    p.out = out; p.out_ld = out_ld; p.out_kind = out_kind; p.scale = (float)scale; p.weight = (float)weight;
-    p.nrows = 0;
-    if (dir < 0) {
-        if (N == 512) return launch_focus<512, false>(h, p, st);
-        if (N == 1024) return launch_focus<1024, false>(h, p, st);
-        return launch_focus<2048, false>(h, p, st);
+    PB_TRY(ensure_scratch(h, 0, (size_t)per * 2 * N * N * sizeof(float2), &tmp));
+    const size_t in_elt = in_kind == PB_IN_COMPLEX ? sizeof(float2) : sizeof(float);
+    const size_t amp_elt = amp_kind == PB_AMP_U8 ? 1 : sizeof(float);
+    const size_t out_elt = out_kind == PB_OUT_COMPLEX ? sizeof(float2) : sizeof(float);
+    for (int b0 = 0; b0 < batch; b0 += per) {
+        const int nb = std::min(per, batch - b0);
+        FocusParams p;
+        p.in = reinterpret_cast<const char*>(in) + (size_t)b0 * in_bs * in_elt;
+        p.in_kind = in_kind;
+        p.amp = amp ? reinterpret_cast<const char*>(amp) + (size_t)b0 * amp_bs * amp_elt : nullptr;
+        p.amp_kind = amp_kind; p.kturns = kturns; p.in_ld = in_ld;
+        p.tmp = reinterpret_cast<float2*>(tmp);
+        p.plan = nullptr;
+        p.out = reinterpret_cast<char*>(out) + (size_t)b0 * out_bs * out_elt;
+        p.out_ld = out_ld; p.out_kind = out_kind; p.scale = (float)scale; p.weight = (float)weight;
+        p.nrows = 0;
+        p.in_bs = in_bs; p.amp_bs = amp_bs; p.out_bs = out_bs;
+        int rc;
+        if (dir < 0) rc = N == 512 ? launch_focus<512, false>(h, p, nb, st) : N == 1024 ? launch_focus<1024, false>(h, p, nb, st) : launch_focus<2048, false>(h, p, nb, st);
+        else rc = N == 512 ? launch_focus<512, true>(h, p, nb, st) : N == 1024 ? launch_focus<1024, true>(h, p, nb, st) : launch_focus<2048, true>(h, p, nb, st);
+        if (rc != PB_OK) return rc;
     }
-    if (N == 512) return launch_focus<512, true>(h, p, st);
-    if (N == 1024) return launch_focus<1024, true>(h, p, st);
-    return launch_focus<2048, true>(h, p, st);
+    return PB_OK;
+}
+
+int try_tuned_fft2(Handle* h, int dtype, const void* in, int in_kind, const void* amp, int amp_kind, double kturns,
+                   int ny, int nx, long long in_ld, int ky, int kx, int dir, double scale, int shift_in, int shift_out,
+                   void* out, int out_kind, double weight, int oy, int ox, long long out_ld, cudaStream_t st) {
+    return try_tuned_fft2_batch(h, dtype, in, in_kind, amp, amp_kind, kturns, 1, 0, 0, ny, nx, in_ld, ky, kx, dir, scale,
+                                shift_in, shift_out, out, out_kind, weight, oy, ox, out_ld, 0, st);
 }
 
 int try_tuned_angular_spectrum(Handle*, int, const void*, int, int, int, int, const void*, const void*, const void*,

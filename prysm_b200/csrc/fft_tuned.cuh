@@ -13,6 +13,11 @@ int try_tuned_fft2(Handle* h, int dtype, const void* in, int in_kind, const void
                    int shift_out, void* out, int out_kind, double weight, int oy, int ox, long long out_ld,
                    cudaStream_t st);
 
+int try_tuned_fft2_batch(Handle* h, int dtype, const void* in, int in_kind, const void* amp, int amp_kind, double kturns,
+                         int batch, long long in_bs, long long amp_bs, int ny, int nx, long long in_ld, int ky, int kx,
+                         int dir, double scale, int shift_in, int shift_out, void* out, int out_kind, double weight,
+                         int oy, int ox, long long out_ld, long long out_bs, cudaStream_t st);
+
 int try_tuned_angular_spectrum(Handle* h, int dtype, const void* in, int ny, int nx, int ky, int kx, const void* ty,
                                const void* tx, const void* tf, int conj_tf, void* out, int oy, int ox,
                                cudaStream_t st);

@@ -47,6 +47,9 @@ def focus(wavefunction, Q):
     """Pupil -> PSF plane: fftshift(fft2(ifftshift(pad2d(w, Q)), norm='ortho')) as one fused call
     (prysm/propagation/fft.py:7-25)."""
     w = _field(wavefunction)
+    if w.ndim == 3:          # a stack of independent fields (B, ny, nx): one batched call (the reference is 2-D only)
+        ky, kx = _padded_shape(w.shape[1:], Q)
+        return _ops.fft2_batch(w, (ky, kx), dir=-1, scale=1.0 / math.sqrt(ky * kx), shift_in=True, shift_out=True)
     ky, kx = _padded_shape(w.shape, Q)
     return _ops.fft2(w, (ky, kx), dir=-1, scale=1.0 / math.sqrt(ky * kx), shift_in=True, shift_out=True)
 
@@ -54,6 +57,9 @@ def focus(wavefunction, Q):
 def unfocus(wavefunction, Q):
     """PSF -> pupil plane, the same with ifft2 (prysm/propagation/fft.py:48-65)."""
     w = _field(wavefunction)
+    if w.ndim == 3:
+        ky, kx = _padded_shape(w.shape[1:], Q)
+        return _ops.fft2_batch(w, (ky, kx), dir=+1, scale=1.0 / math.sqrt(ky * kx), shift_in=True, shift_out=True)
     ky, kx = _padded_shape(w.shape, Q)
     return _ops.fft2(w, (ky, kx), dir=+1, scale=1.0 / math.sqrt(ky * kx), shift_in=True, shift_out=True)
 

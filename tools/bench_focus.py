@@ -46,3 +46,19 @@ e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (reps * B)
 print(f'variant {os.environ.get("PB_FOCUS_PHASES_PER_LAUNCH", "1")} tuned_disabled={os.environ.get("PB_DISABLE_TUNED") is not None}: '
       f'{us:.1f} us/propagation  {1e6 / us:.0f} prop/s  {167772160 / us / 1e3:.0f} GB/s algorithmic  frac {167772160 / us / 1e3 / 6571.2:.3f}')
+
+# batched form: all B pupils in one pb_fft2_batch call (fields share launches, PB_FOCUS_BATCH per launch pair)
+stack = torch.stack(ins)
+out_b = torch.empty((B, K, K), dtype=torch.complex64, device='cuda')
+def step_b():
+    _ops.fft2_batch(stack, (K, K), dir=-1, scale=1.0 / K, shift_in=True, shift_out=True, out=out_b)
+for _ in range(3): step_b()
+torch.cuda.synchronize()
+ref = _ops.fft2(ins[5], (K, K), dir=-1, scale=1.0 / K, shift_in=True, shift_out=True)
+print('batched == single:', bool(torch.equal(out_b[5], ref)), bool(torch.equal(out_b[15], _ops.fft2(ins[15], (K, K), dir=-1, scale=1.0 / K, shift_in=True, shift_out=True))))
+e0.record()
+for _ in range(reps): step_b()
+e1.record(); torch.cuda.synchronize()
+us = e0.elapsed_time(e1) * 1e3 / (reps * B)
+print(f'batched, PB_FOCUS_BATCH={os.environ.get("PB_FOCUS_BATCH", "2")}: {us:.1f} us/propagation  {1e6 / us:.0f} prop/s  '
+      f'{167772160 / us / 1e3:.0f} GB/s algorithmic  frac {167772160 / us / 1e3 / 6571.2:.3f}')
