@@ -60,5 +60,5 @@ e0.record()
 for _ in range(reps): step_b()
 e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (reps * B)
-print(f'batched, PB_FOCUS_BATCH={os.environ.get("PB_FOCUS_BATCH", "2")}: {us:.1f} us/propagation  {1e6 / us:.0f} prop/s  '
+print(f'batched, PB_FOCUS_BATCH={os.environ.get("PB_FOCUS_BATCH", "8 (default)")}: {us:.1f} us/propagation  {1e6 / us:.0f} prop/s  '
       f'{167772160 / us / 1e3:.0f} GB/s algorithmic  frac {167772160 / us / 1e3 / 6571.2:.3f}')
