@@ -178,10 +178,13 @@ class CZT:
         Kx, Ky = next_fast_len(Nx + Mx - 1), next_fast_len(Ny + My - 1)
         # the chirps, phase ramps and kernel spectra are built on the device from ten scalars per axis
         # (fp64 phases): constructing an executor per wavelength costs no host maths and no uploads
-        self._bx, self._postx, self._Hx, self._Hadjx = _ops.czt_plan(
-            Nx, Mx, Kx, float(fx[Mx // 2]) / dfx, dx * dfx, sign, float(x[Nx // 2]), float(fx[0]), dfx, cd, dev)
-        self._by, self._posty, self._Hy, self._Hadjy = _ops.czt_plan(
-            Ny, My, Ky, float(fy[My // 2]) / dfy, dy * dfy, sign, float(y[Ny // 2]), float(fy[0]), dfy, cd, dev)
+        px = (Nx, Mx, Kx, float(fx[Mx // 2]) / dfx, dx * dfx, sign, float(x[Nx // 2]), float(fx[0]), dfx)
+        py = (Ny, My, Ky, float(fy[My // 2]) / dfy, dy * dfy, sign, float(y[Ny // 2]), float(fy[0]), dfy)
+        self._bx, self._postx, self._Hx, self._Hadjx = _ops.czt_plan(*px, cd, dev)
+        if py == px:   # square, centred geometry (every BASELINE config): one plan serves both axes
+            self._by, self._posty, self._Hy, self._Hadjy = self._bx, self._postx, self._Hx, self._Hadjx
+        else:
+            self._by, self._posty, self._Hy, self._Hadjy = _ops.czt_plan(*py, cd, dev)
         self._Nx, self._Ny, self._Mx, self._My, self._Kx, self._Ky = Nx, Ny, Mx, My, Kx, Ky
         x_first_cost = Ny * Kx * math.log2(Kx) + Mx * Ky * math.log2(Ky)
         y_first_cost = Nx * Ky * math.log2(Ky) + My * Kx * math.log2(Kx)
@@ -222,8 +225,8 @@ class CZT:
         return back_y(back_x(o, 1.0), self.norm)
 
     def nbytes(self):
-        return sum(v.numel() * v.element_size() for v in (self._bx, self._Hx, self._postx, self._Hadjx,
-                                                          self._by, self._Hy, self._posty, self._Hadjy))
+        vs = {id(v): v for v in (self._bx, self._Hx, self._postx, self._Hadjx, self._by, self._Hy, self._posty, self._Hadjy)}
+        return sum(v.numel() * v.element_size() for v in vs.values())
 
 
 def _uniform_spacing(values, name):
