@@ -80,3 +80,26 @@ def test_czt_axis_plan_matches_oracle_basis():
     assert np.allclose(ax.b, b, atol=1e-14) and np.allclose(ax.post, a, atol=1e-14)
     assert np.allclose(ax.H, H, atol=1e-12)
     assert ax.K == 32 and math.log2(ax.K).is_integer()
+
+
+def test_widened_rows_host_checks_need_no_gpu():
+    """Argument checks of the SURVEY 8(f) rows that fire before any kernel launch (reference messages)."""
+    from prysm_b200 import coronagraph, polynomials
+    with pytest.raises(TypeError, match='charge must be an integer'):
+        coronagraph.vortex_phase_mask(2.5)
+    assert callable(coronagraph.vortex_phase_mask(np.int64(2)))
+    with pytest.raises(ValueError, match='requires field_at_fpm'):
+        coronagraph.to_fpm_and_back_adjoint(None, None, None, return_fpm_grad=True)
+    with pytest.raises(ValueError, match='requires field_at_fpm'):
+        coronagraph.to_fpm_and_back_multiresolution_adjoint(None, None, None, return_fpm_grad=True)
+    with pytest.raises(ValueError, match='requires field_at_lyot'):
+        coronagraph.babinet_adjoint(None, None, None, None, return_lyot_grad=True)
+    with pytest.raises(ValueError, match='two positive values'):
+        fttools.fourier_resample(np.ones((4, 4)), (1, -1))
+    a = np.ones((4, 4))
+    assert fttools.fourier_resample(a, 1) is a
+    import prysm_oracle as O
+    assert [polynomials.noll_to_nm(j) for j in range(1, 80)] == [O.noll_to_nm(j) for j in range(1, 80)]
+    assert polynomials.fringe_to_nm(1) == (0, 0) and polynomials.fringe_to_nm(4) == (2, 0)
+    assert polynomials.zernike_norm(4, 0) == pytest.approx(math.sqrt(5))
+    assert propagation.MultiResolutionExecutor([1, 2], [3, 4], [5, 6], [7, 8]).__len__() == 2
