@@ -1,7 +1,7 @@
 """GPU: correctness of the tuned focus kernels against the oracle + timing of one variant (env-selected)."""
 import os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import prysm_oracle as O
 import prysm_b200 as pb

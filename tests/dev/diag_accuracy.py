@@ -1,7 +1,7 @@
 """GPU diagnostic: accuracy of the library's c64 FFT passes vs an fp64 FFT (and cuFFT's c64 for scale)."""
 import sys, os
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import prysm_b200 as pb
 from prysm_b200 import _ops

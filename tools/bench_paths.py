@@ -2,7 +2,7 @@
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, ROOT)
 import prysm_b200 as pb
 from prysm_b200 import _ops, propagation as P
 from prysm_b200.polychromatic import polychromatic_psf
