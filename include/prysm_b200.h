@@ -257,6 +257,13 @@ int pb_encircled_energy_adjoint_seed(pb_handle_t h, int dtype, int ny, int nx, d
  * (prysm/propagation/coronagraph.py:102-132). */
 int pb_vortex_phase(pb_handle_t h, int dtype, int charge, const void* xf, const void* yf,
                     long long count, void* out, void* stream);
+/* out = bilinear interpolation of the complex `map` (ny, nx) at col = (xf - cx)/dx + nx/2, row = (yf - cy)/dx + ny/2 with
+ * edge replication, and `fill` (a complex array like out, or the scalar (fill_re, fill_im) when NULL) where a coordinate
+ * leaves [0, n-1]: the fpm(xf, yf) callable of prepare_measured_fpm at order=1
+ * (prysm/propagation/coronagraph.py:135-209; scipy.ndimage.map_coordinates(order=1, mode='nearest')). */
+int pb_resample_bilinear(pb_handle_t h, int dtype, const void* map, int ny, int nx, const void* xf,
+                         const void* yf, long long count, double cx, double cy, double dx, const void* fill,
+                         double fill_re, double fill_im, void* out, void* stream);
 /* one level of prepare_multiresolution (prysm/propagation/dft.py:155-167, 262-292): focal grids
  * xf = (ix - nx/2)*fdx + shift, yf likewise, and the hand-off window
  * taper(r; a0, b0) - taper(r; a1, b1), taper = 1 - smootherstep((r - a)/(b - a));

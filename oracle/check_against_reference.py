@@ -227,6 +227,13 @@ for prec, rdt, cdt, eps in ((64, np.float64, np.complex128, 1e-13), (32, np.floa
     cz[3] = 0
     check(tag + 'zernike_sum', O.zernike_sum(cz, nms, xo, yo), pz_sum(cz, nms, xr, yr), eps * 10)
 
+    # ---- measured focal-plane mask resampling
+    mm = crand(rng, (21, 17), cdt)
+    qx = (rng.random((9, 11)) * 12 - 6).astype(rdt)
+    qy = (rng.random((9, 11)) * 12 - 6).astype(rdt)
+    for kw in (dict(charge=2), dict(fill=0.25), dict()):
+        check(tag + f'prepare_measured_fpm {kw}', O.prepare_measured_fpm(mm, 0.4, (0.3, -0.2), **kw)(qx, qy),
+              propagation.prepare_measured_fpm(mm, 0.4, center=(0.3, -0.2), **kw)(qx, qy), eps)
     # ---- image-chain consumers (rank 4)
     from prysm import convolution as pconv
     ob = rng.random((12, 10)).astype(rdt)

@@ -231,6 +231,14 @@ def coronagraph():
             if kind == 'mdft':
                 g.update({f'mr_win{k}': mr.windows[k], f'mr_xf{k}': mr.xf[k], f'mr_yf{k}': mr.yf[k]})
     g['mr_vortex1'] = fpm(mr.xf[1], mr.yf[1])
+    # measured-mask resampling (reference tests/test_propagation.py:648-676)
+    mm = crand(rng, (41, 37))
+    qx = rng.random((24, 30)) * 20 - 10
+    qy = rng.random((24, 30)) * 20 - 10
+    g.update(mf_map=mm, mf_qx=qx, mf_qy=qy,
+             mf_vortex=propagation.prepare_measured_fpm(mm, 0.4, center=(0.3, -0.2), charge=2)(qx, qy),
+             mf_scalar=propagation.prepare_measured_fpm(mm, 0.4, center=(0.3, -0.2), fill=0.25)(qx, qy),
+             mf_default=propagation.prepare_measured_fpm(mm, 0.4)(qx, qy))
     np.savez_compressed(os.path.join(OUT, 'coronagraph.npz'), **g)
     print(f'coronagraph.npz written, {len(g)} arrays')
 

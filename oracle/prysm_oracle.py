@@ -707,6 +707,28 @@ def vortex_phase_mask(charge):
     return fpm
 
 
+def prepare_measured_fpm(measurement, dx, center=(0, 0), charge=None, fill=None, order=1):
+    """fpm(xf, yf): spline-interpolate a measured complex mask at col = (xf-cx)/dx + nx//2, row = (yf-cy)/dx + ny//2
+    (scipy.ndimage.map_coordinates, mode='nearest'), `fill` (default: ideal vortex if charge is given, else 1) outside
+    the measured extent.  prysm/propagation/coronagraph.py:135-209."""
+    from scipy import ndimage
+    meas = np.asarray(measurement)
+    ny, nx = meas.shape
+    cx, cy = center
+    if fill is None:
+        fill = vortex_phase_mask(charge) if charge is not None else 1.0
+
+    def fpm(xf, yf):
+        col = (xf - cx) / dx + nx // 2
+        row = (yf - cy) / dx + ny // 2
+        coords = np.stack([row.reshape(-1), col.reshape(-1)])
+        ri = ndimage.map_coordinates(np.real(meas), coords, order=order, mode='nearest')
+        ii = ndimage.map_coordinates(np.imag(meas), coords, order=order, mode='nearest')
+        inside = (row >= 0) & (row <= ny - 1) & (col >= 0) & (col <= nx - 1)
+        return np.where(inside, (ri + 1j * ii).reshape(xf.shape), fill(xf, yf) if callable(fill) else fill)
+    return fpm
+
+
 def smootherstep(t):
     """6t^5 - 15t^4 + 10t^3 on clip(t, 0, 1).  prysm/propagation/dft.py:155-158."""
     t = np.clip(t, 0, 1)

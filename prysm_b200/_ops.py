@@ -528,6 +528,25 @@ def vortex_phase(charge, xf, yf):
     return out
 
 
+def resample_bilinear(cmap, xf, yf, cx, cy, dx, fill):
+    """Bilinear, edge-replicating resampling of a complex map at focal coordinates; `fill` (tensor or scalar) outside."""
+    xf = xf.contiguous()
+    yf = yf.to(xf.dtype).contiguous()
+    cd = _CPLX_OF[xf.dtype]
+    cmap = cmap.to(cd).contiguous()
+    ny, nx = cmap.shape
+    fill_t, fs = None, 0j
+    if isinstance(fill, torch.Tensor):
+        fill_t = ascomplex(fill).to(cd).expand(xf.shape).contiguous()
+    else:
+        fs = complex(fill)
+    out = torch.empty(xf.shape, dtype=cd, device=xf.device)
+    h, st = _ctx(xf)
+    h.check(lib.pb_resample_bilinear(h.ptr, _CODE[cd], _p(cmap), ny, nx, _p(xf), _p(yf), xf.numel(), float(cx), float(cy),
+                                     float(dx), _p(fill_t), fs.real, fs.imag, _p(out), st))
+    return out
+
+
 def radial_window(shape, fdx, shift, here, nxt, rdtype, dev):
     """(window, xf, yf) of one multi-resolution level (pb_radial_window); here / nxt = (a, b) or None."""
     ny, nx = shape

@@ -72,6 +72,29 @@ def vortex_phase_mask(charge):
     return _VortexMask(charge)
 
 
+def prepare_measured_fpm(measurement, dx, center=(0, 0), charge=None, fill=None, order=1):
+    """Wrap a measured complex focal-plane-mask map as an fpm(xf, yf) callable for the multi-resolution executor
+    (prysm/propagation/coronagraph.py:135-209): each level resamples the map at its own focal grid in one kernel --
+    bilinear (order=1, the reference's default; higher spline orders are not on the device), edge-replicating, with
+    `fill` (scalar or callable; default an ideal charge-`charge` vortex, else 1) outside the measured extent."""
+    if order != 1:
+        raise NotImplementedError('only order=1 (bilinear, the reference default) resampling runs on the device')
+    meas = _field(measurement)
+    cx, cy = center
+    if fill is None:
+        fill = vortex_phase_mask(charge) if charge is not None else 1.0
+
+    def fpm(xf, yf):
+        xf = _ops.asdevice(xf)
+        yf = _ops.asdevice(yf)
+        if xf.dtype not in (torch.float32, torch.float64):
+            xf = xf.to(torch.float64)
+        fillv = _ops.asdevice(fill(xf, yf)) if callable(fill) else fill
+        return _ops.resample_bilinear(meas, xf, yf, cx, cy, dx, fillv)
+
+    return fpm
+
+
 def to_fpm_and_back_multiresolution(wavefunction, fpm, executor, return_more=False):
     """Sum over levels of unfocus_dft(focus_dft(w) * fpm(xf, yf) * window) (prysm/propagation/coronagraph.py:212-251).
     The mask, the window and the product are one pass; the level sum is a fused accumulate."""

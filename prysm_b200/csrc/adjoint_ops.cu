@@ -208,6 +208,30 @@ __global__ void vortex_kernel(int charge, const R* __restrict__ xf, const R* __r
     }
 }
 
+// Bilinear resampling of a complex map at col = (xf - cx)/dx + nx/2, row = (yf - cy)/dx + ny/2 with edge replication
+// (scipy.ndimage.map_coordinates(order=1, mode='nearest')), `fill` outside [0, n-1] on either axis
+// (prysm/propagation/coronagraph.py:192-207).
+template <typename R>
+__global__ void resample_bilinear_kernel(const cplx<R>* __restrict__ map, int ny, int nx, const R* __restrict__ xf,
+                                         const R* __restrict__ yf, long long n, double cx, double cy, double dx,
+                                         const cplx<R>* __restrict__ fill, cplx<R> fill_s, cplx<R>* __restrict__ out) {
+    PB_GRID_STRIDE(i, n) {
+        const double col = ((double)xf[i] - cx) / dx + (double)(nx / 2);
+        const double row = ((double)yf[i] - cy) / dx + (double)(ny / 2);
+        const bool inside = row >= 0.0 && row <= (double)(ny - 1) && col >= 0.0 && col <= (double)(nx - 1);
+        if (!inside) { out[i] = fill ? fill[i] : fill_s; continue; }
+        const double fr = floor(row), fc = floor(col);
+        const int r0 = (int)fr, c0 = (int)fc;
+        const int r1 = min(r0 + 1, ny - 1), c1 = min(c0 + 1, nx - 1);
+        const double wr = row - fr, wc = col - fc;
+        const cplx<R> a = map[(long long)r0 * nx + c0], b = map[(long long)r0 * nx + c1];
+        const cplx<R> c = map[(long long)r1 * nx + c0], d = map[(long long)r1 * nx + c1];
+        const double re = (1 - wr) * ((1 - wc) * a.x + wc * b.x) + wr * ((1 - wc) * c.x + wc * d.x);
+        const double im = (1 - wr) * ((1 - wc) * a.y + wc * b.y) + wr * ((1 - wc) * c.y + wc * d.y);
+        out[i] = mk<R>((R)re, (R)im);
+    }
+}
+
 __device__ inline float mul_add_rn(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }     // two roundings,
 __device__ inline double mul_add_rn(double a, double b, double c) { return __dadd_rn(__dmul_rn(a, b), c); }  // like numpy
 
@@ -378,6 +402,23 @@ extern "C" int pb_vortex_phase(pb_handle_t hh, int dtype, int charge, const void
     const int g = grid_for(count, 256, h->sm_count);
     if (dtype == PB_C64) vortex_kernel<float><<<g, 256, 0, st>>>(charge, (const float*)xf, (const float*)yf, count, (float2*)out);
     else vortex_kernel<double><<<g, 256, 0, st>>>(charge, (const double*)xf, (const double*)yf, count, (double2*)out);
+    PB_LAUNCH_CHECK(h);
+    return PB_OK;
+}
+
+extern "C" int pb_resample_bilinear(pb_handle_t hh, int dtype, const void* map, int ny, int nx, const void* xf, const void* yf,
+                                    long long count, double cx, double cy, double dx, const void* fill, double fill_re,
+                                    double fill_im, void* out, void* stream) {
+    PB_HANDLE(hh);
+    if (!map || !xf || !yf || !out || ny < 1 || nx < 1 || dx == 0.0) return fail(h, PB_ERR_INVALID, "bad resample arguments");
+    if (count <= 0) return PB_OK;
+    const int g = grid_for(count, 256, h->sm_count);
+    if (dtype == PB_C64)
+        resample_bilinear_kernel<float><<<g, 256, 0, st>>>((const float2*)map, ny, nx, (const float*)xf, (const float*)yf, count, cx, cy, dx,
+                                                            (const float2*)fill, make_float2((float)fill_re, (float)fill_im), (float2*)out);
+    else
+        resample_bilinear_kernel<double><<<g, 256, 0, st>>>((const double2*)map, ny, nx, (const double*)xf, (const double*)yf, count, cx, cy,
+                                                             dx, (const double2*)fill, make_double2(fill_re, fill_im), (double2*)out);
     PB_LAUNCH_CHECK(h);
     return PB_OK;
 }

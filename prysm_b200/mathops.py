@@ -27,7 +27,7 @@ _PROPAGATION_FUNCS = (
 )
 _CORONAGRAPH_FUNCS = (
     'to_fpm_and_back', 'to_fpm_and_back_adjoint', 'to_fpm_and_back_multiresolution',
-    'to_fpm_and_back_multiresolution_adjoint', 'babinet', 'babinet_adjoint', 'vortex_phase_mask',
+    'to_fpm_and_back_multiresolution_adjoint', 'babinet', 'babinet_adjoint', 'vortex_phase_mask', 'prepare_measured_fpm',
 )
 _TARGETS = {
     'prysm.propagation.fft': {n: getattr(_prop, n) for n in ('focus', 'unfocus', 'focus_adjoint', 'unfocus_adjoint')},
@@ -39,7 +39,7 @@ _TARGETS = {
         'prepare_multiresolution': _prop.prepare_multiresolution, 'MultiResolutionExecutor': _prop.MultiResolutionExecutor},
     'prysm.propagation.coronagraph': {n: getattr(_prop, n) for n in _CORONAGRAPH_FUNCS},
     'prysm.propagation.wavefront': {**{n: getattr(_prop, n) for n in _PROPAGATION_FUNCS + _CORONAGRAPH_FUNCS if n not in (
-        'angular_spectrum_transfer_function', 'coordinates_for_focus', 'vortex_phase_mask')},
+        'angular_spectrum_transfer_function', 'coordinates_for_focus', 'vortex_phase_mask', 'prepare_measured_fpm')},
         'prepare_multiresolution': _prop.prepare_multiresolution, 'pad2d': _ft.pad2d, 'crop_center': _ft.crop_center},
     'prysm.propagation': {**{n: getattr(_prop, n) for n in _PROPAGATION_FUNCS + _CORONAGRAPH_FUNCS},
                           'prepare_multiresolution': _prop.prepare_multiresolution,

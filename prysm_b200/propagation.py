@@ -22,7 +22,7 @@ from .conf import config
 from .fttools import pad2d, crop_center, MDFT, CZT, FFTDFT
 from .coronagraph import (  # noqa: F401  (re-exported like prysm/propagation/__init__.py)
     to_fpm_and_back, to_fpm_and_back_adjoint, to_fpm_and_back_multiresolution,
-    to_fpm_and_back_multiresolution_adjoint, babinet, babinet_adjoint, vortex_phase_mask,
+    to_fpm_and_back_multiresolution_adjoint, babinet, babinet_adjoint, vortex_phase_mask, prepare_measured_fpm,
 )
 
 

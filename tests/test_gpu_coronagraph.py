@@ -311,3 +311,42 @@ def test_tensor_core_mdft_adjoint_and_round_trip(pb, shape):
     ref = O.to_fpm_and_back(a.astype(np.complex128), fpm.astype(np.float64), exo)
     assert rel_linf(host(P.to_fpm_and_back(a, fpm, ex)), ref) < 3e-6
     pb.config.precision = 64
+
+
+@pytest.mark.parametrize('prec', [64, 32])
+def test_measured_fpm_resampling(pb, gold, prec):
+    """prepare_measured_fpm at order=1 against the reference (scipy.ndimage.map_coordinates) and inside the
+    multi-resolution stack."""
+    rdt, cdt, tol = setprec(pb, prec)
+    g = gold
+    P = pb.propagation
+    mm, qx, qy = g['mf_map'].astype(cdt), g['mf_qx'].astype(rdt), g['mf_qy'].astype(rdt)
+    # fp32 coordinates move the sample points by ~1e-6 of a pixel: compare at 1e-5 of the map's scale
+    ftol = 1e-12 if prec == 64 else 2e-5
+    assert rel_linf(host(P.prepare_measured_fpm(mm, 0.4, center=(0.3, -0.2), charge=2)(qx, qy)), g['mf_vortex']) < ftol
+    assert rel_linf(host(P.prepare_measured_fpm(mm, 0.4, center=(0.3, -0.2), fill=0.25)(qx, qy)), g['mf_scalar']) < ftol
+    assert rel_linf(host(P.prepare_measured_fpm(mm, 0.4)(qx, qy)), g['mf_default']) < ftol
+    with pytest.raises(NotImplementedError):
+        P.prepare_measured_fpm(mm, 0.4, order=3)
+    # reference tests/test_propagation.py:648-676: exact on its own grid, ideal vortex beyond, scalar fill
+    x, y = O.make_xy_grid(129, dx=0.4)
+    meas = np.exp(1j * 2 * np.arctan2(y, x))
+    f = P.prepare_measured_fpm(meas.astype(cdt), 0.4, charge=2)
+    assert np.abs(host(f(x.astype(rdt), y.astype(rdt))) - meas).max() < (1e-12 if prec == 64 else 2e-5)
+    far = np.full((1, 1), 1e5, dtype=rdt)
+    assert np.abs(host(f(far, far)) - np.exp(1j * 2 * np.arctan2(1e5, 1e5))).max() < (1e-12 if prec == 64 else 1e-6)
+    assert complex(host(P.prepare_measured_fpm(np.ones((65, 65), dtype=cdt), 1.0, fill=0.0)(np.full((1, 1), 1e3, dtype=rdt),
+                                                                                             np.full((1, 1), 1e3, dtype=rdt)))[0, 0]) == 0
+    # a measured copy of the ideal vortex drives the multi-resolution stack to the ideal-mask result where it is sampled
+    pb.config.precision = 64
+    mex = P.prepare_multiresolution(0.1, 64, 2.0, 32, HeNe, 10.0, num_levels=2, fine_samples=32)
+    xm, ym = O.make_xy_grid(1025, dx=0.05)
+    measured = P.prepare_measured_fpm(np.exp(1j * 2 * np.arctan2(ym, xm)), 0.05, charge=2)
+    rng = np.random.default_rng(3)
+    w = rng.standard_normal((64, 64)) + 1j * rng.standard_normal((64, 64))
+    a = host(P.to_fpm_and_back_multiresolution(w, measured, mex))
+    b = host(P.to_fpm_and_back_multiresolution(w, P.vortex_phase_mask(2), mex))
+    assert rel_linf(a, b) < 1e-10         # the level grids fall on samples of the 0.05 um map: interpolation is exact
+    mo = O.prepare_multiresolution(0.1, 64, 2.0, 32, HeNe, 10.0, num_levels=2, fine_samples=32)
+    ref = O.to_fpm_and_back_multiresolution(w, O.prepare_measured_fpm(np.exp(1j * 2 * np.arctan2(ym, xm)), 0.05, charge=2), mo)
+    assert rel_linf(a, ref) < 1e-11

@@ -100,3 +100,18 @@ def test_windows_partition_unity():
     with pytest.raises(TypeError):
         O.vortex_phase_mask(2.5)
     O.vortex_phase_mask(np.int64(2))
+
+
+def test_measured_fpm_resampling(gold):
+    """prepare_measured_fpm (coronagraph.py:135-209) incl. the reference's own identities (tests/test_propagation.py:648-676)."""
+    g = gold
+    mm, qx, qy = g['mf_map'], g['mf_qx'], g['mf_qy']
+    assert rel_linf(O.prepare_measured_fpm(mm, 0.4, (0.3, -0.2), charge=2)(qx, qy), g['mf_vortex']) < 1e-14
+    assert rel_linf(O.prepare_measured_fpm(mm, 0.4, (0.3, -0.2), fill=0.25)(qx, qy), g['mf_scalar']) < 1e-14
+    assert rel_linf(O.prepare_measured_fpm(mm, 0.4)(qx, qy), g['mf_default']) < 1e-14
+    x, y = O.make_xy_grid(129, dx=0.4)
+    meas = np.exp(1j * 2 * np.arctan2(y, x))
+    f = O.prepare_measured_fpm(meas, 0.4, charge=2)
+    assert np.allclose(f(x, y), meas, atol=1e-12)
+    far = np.full((1, 1), 1e5)
+    assert np.allclose(f(far, far), np.exp(1j * 2 * np.arctan2(far, far)), atol=1e-12)
