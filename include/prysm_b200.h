@@ -316,6 +316,18 @@ int pb_pack_complex(pb_handle_t h, int dtype, const void* re, const void* im, co
 int pb_packed_spectrum_product(pb_handle_t h, int dtype, const void* Z, int ny, int nx, double scale,
                                const double* im_scale_dev, void* out, void* stream);
 
+/* detector sampling of the image chain (prysm/detector.py:151-338), real arrays:
+ * pb_bindown: out (ny/fy, nx/fx) = sum (mean != 0: mean) of each fy x fx block (bindown);
+ * pb_tile:    out (ny*fy, nx*fx) = scale * in[y/fy, x/fx] (tile, the adjoint of bindown);
+ * pb_separable_tf: out[y,x] = sinc(fx[x] wx) sinc(fy[y] wy) (kind 0, pixel_ft) or cos(2 wx fx[x]) cos(2 wy fy[y])
+ *              (kind 1, olpf_ft) from the two frequency VECTORS. */
+int pb_bindown(pb_handle_t h, int dtype, const void* in, int ny, int nx, int fy, int fx, int mean,
+               void* out, void* stream);
+int pb_tile(pb_handle_t h, int dtype, const void* in, int ny, int nx, int fy, int fx, double scale,
+            void* out, void* stream);
+int pb_separable_tf(pb_handle_t h, int dtype, int kind, const void* fx, const void* fy, int ny, int nx,
+                    double wx, double wy, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -227,6 +227,16 @@ for prec, rdt, cdt, eps in ((64, np.float64, np.complex128, 1e-13), (32, np.floa
     cz[3] = 0
     check(tag + 'zernike_sum', O.zernike_sum(cz, nms, xo, yo), pz_sum(cz, nms, xr, yr), eps * 10)
 
+    # ---- detector sampling
+    from prysm import detector as pdet
+    img = rng.random((12, 18)).astype(rdt)
+    for fac in (2, 3, (2, 3), (4, 6)):
+        for mode in ('avg', 'sum'):
+            check(tag + f'bindown {fac} {mode}', O.bindown(img, fac, mode), pdet.bindown(img, fac, mode), eps)
+            check(tag + f'tile {fac} {mode}', O.tile(img, fac, mode), pdet.tile(img, fac, mode), eps)
+    gfx, gfy = O.transfer_function_grids((12, 18), 2.0, False, rdt)[:2]
+    check(tag + 'pixel_ft', O.pixel_ft(gfx, gfy, 3.0, 2.5), pdet.pixel_ft(gfx, gfy, 3.0, 2.5), eps)
+    check(tag + 'olpf_ft', O.olpf_ft(gfx, gfy, 0.7, 0.9), pdet.olpf_ft(gfx, gfy, 0.7, 0.9), eps)
     # ---- measured focal-plane mask resampling
     mm = crand(rng, (21, 17), cdt)
     qx = (rng.random((9, 11)) * 12 - 6).astype(rdt)

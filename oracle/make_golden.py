@@ -304,6 +304,14 @@ def imagechain():
     for i, zoom in enumerate((0.5, 2, (2, 1.5))):
         g[f'resample{i}'] = fttools.fourier_resample(ob, zoom)
     g['resample_c'] = fttools.fourier_resample(obc, 2)
+    from prysm import detector
+    for i, fac in enumerate((2, 3, (2, 3), (4, 6))):
+        g[f'bin{i}_avg'] = detector.bindown(ob, fac, 'avg')
+        g[f'bin{i}_sum'] = detector.bindown(ob, fac, 'sum')
+        g[f'tile{i}_sum'] = detector.tile(ps[:6, :5], fac, 'sum')
+    ufy, ufx = (fttools.forward_ft_unit(2.0, n, shift=False) for n in ob.shape)
+    g['pixel_ft'] = detector.pixel_ft(ufx.reshape(1, -1), ufy.reshape(-1, 1), 3.0, 2.5)
+    g['olpf_ft'] = detector.olpf_ft(ufx.reshape(1, -1), ufy.reshape(-1, 1), 0.7, 0.9)
     np.savez_compressed(os.path.join(OUT, 'imagechain.npz'), **g)
     print(f'imagechain.npz written, {len(g)} arrays')
 

@@ -901,6 +901,41 @@ def fourier_resample(f, zoom, rdtype=np.float64):
     return out if np.iscomplexobj(f) else out.real
 
 
+def bindown(array, factor, mode='avg'):
+    """Block mean / sum over factor x factor samples (2-D).  prysm/detector.py:222-274."""
+    fy, fx = (factor, factor) if np.ndim(factor) == 0 else factor
+    m, n = array.shape
+    view = array.reshape(m // fy, fy, n // fx, fx)
+    if mode.lower() in ('avg', 'average', 'mean'):
+        return view.mean(axis=(1, 3))
+    if mode.lower() == 'sum':
+        return view.sum(axis=(1, 3))
+    raise ValueError('mode must be average or sum.')
+
+
+def tile(array, factor, scaling='sum'):
+    """Repeat every sample factor x factor times (the adjoint of bindown), scaled by 1/prod(factor) for 'sum'.
+    prysm/detector.py:277-338."""
+    fy, fx = (factor, factor) if np.ndim(factor) == 0 else factor
+    if scaling == 'sum':
+        sf = 1 / (fy * fx)
+    elif scaling in ('avg', 'average', 'mean'):
+        sf = 1
+    else:
+        raise ValueError('scaling must be average or sum')
+    return np.repeat(np.repeat(array, fy, axis=0), fx, axis=1) * sf
+
+
+def pixel_ft(fx, fy, width_x, width_y):
+    """sinc(fx wx) sinc(fy wy).  prysm/detector.py:174-194."""
+    return np.sinc(fx * width_x) * np.sinc(fy * width_y)
+
+
+def olpf_ft(fx, fy, width_x, width_y):
+    """cos(2 wx fx) cos(2 wy fy).  prysm/detector.py:151-171."""
+    return np.cos(2 * width_x * fx) * np.cos(2 * width_y * fy)
+
+
 # --------------------------------------------------------------------------------------
 # pupil synthesis by recurrence -- the step before the path (SURVEY.md 8(f) rank 3)
 # (prysm/coordinates.py:73-102, 344-378; geometry.py:11-34, 337-372; polynomials/jacobi.py:13-175;

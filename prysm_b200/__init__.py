@@ -10,6 +10,7 @@ Mirrors the reference's module layout for the path only:
     prysm_b200.coronagraph  <-> prysm.propagation.coronagraph (re-exported by .propagation like the reference)
     prysm_b200.coordinates / .geometry  <-> prysm.coordinates.make_xy_grid / cart_to_polar, prysm.geometry.circle / antialias
     prysm_b200.convolution  <-> prysm.convolution (conv, apply_transfer_functions)
+    prysm_b200.detector     <-> prysm.detector (bindown, tile, pixel_ft, olpf_ft)
     prysm_b200.graphs       CUDA-graph capture of launch-bound compositions (no reference counterpart)
 Every array operation is a call into libprysm_b200.so (hand-written sm_100a CUDA behind the C ABI
 of include/prysm_b200.h).  Importing this package without the built library raises ImportError.
@@ -17,7 +18,7 @@ of include/prysm_b200.h).  Importing this package without the built library rais
 from . import _capi  # noqa: F401  (fails loudly if the CUDA library is missing)
 from .conf import config  # noqa: F401
 from . import fttools, propagation, coronagraph, otf, psf, polynomials, polychromatic, mathops, graphs  # noqa: F401
-from . import coordinates, geometry, convolution  # noqa: F401
+from . import coordinates, geometry, convolution, detector  # noqa: F401
 from ._capi import B200Error  # noqa: F401
 from .propagation import Wavefront  # noqa: F401
 from ._ops import asdevice, asnumpy, set_device  # noqa: F401

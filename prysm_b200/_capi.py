@@ -70,6 +70,9 @@ SIGNATURES = {
     'pb_pack_complex': (_i, [_vp, _i, _vp, _vp, _vp, _ll, _vp, _vp]),
     'pb_packed_spectrum_product': (_i, [_vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
     'pb_resample_bilinear': (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _ll, _d, _d, _d, _vp, _d, _d, _vp, _vp]),
+    'pb_bindown': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'pb_tile': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
+    'pb_separable_tf': (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _d, _d, _vp, _vp]),
     'pb_radial_window': (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _vp, _vp, _vp, _vp]),
 }
 

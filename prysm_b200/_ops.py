@@ -669,6 +669,41 @@ def packed_spectrum_product(Z, scale=1.0, im_scale=None):
     return out
 
 
+def _real2d(a):
+    a = asdevice(a)
+    if a.dtype not in _CPLX_OF:
+        a = a.to(torch.float32)
+    return a.contiguous()
+
+
+def bindown(a, fy, fx, mean):
+    a = _real2d(a)
+    ny, nx = a.shape
+    out = torch.empty((ny // max(fy, 1), nx // max(fx, 1)), dtype=a.dtype, device=a.device)
+    h, st = _ctx(a)
+    h.check(lib.pb_bindown(h.ptr, _CODE[a.dtype], _p(a), ny, nx, int(fy), int(fx), int(bool(mean)), _p(out), st))
+    return out
+
+
+def tile(a, fy, fx, scale):
+    a = _real2d(a)
+    ny, nx = a.shape
+    out = torch.empty((ny * fy, nx * fx), dtype=a.dtype, device=a.device)
+    h, st = _ctx(a)
+    h.check(lib.pb_tile(h.ptr, _CODE[a.dtype], _p(a), ny, nx, int(fy), int(fx), float(scale), _p(out), st))
+    return out
+
+
+def separable_tf(kind, fx, fy, wx, wy):
+    fx = _real2d(fx).reshape(-1)
+    fy = _real2d(fy).to(fx.dtype).reshape(-1)
+    out = torch.empty((fy.numel(), fx.numel()), dtype=fx.dtype, device=fx.device)
+    h, st = _ctx(fx)
+    h.check(lib.pb_separable_tf(h.ptr, _CODE[fx.dtype], int(kind), _p(fx), _p(fy), fy.numel(), fx.numel(), float(wx), float(wy),
+                                _p(out), st))
+    return out
+
+
 def launch_count(dev=None):
     dev = device() if dev is None else torch.device(dev)
     return capi.launch_count(dev.index)

@@ -67,6 +67,46 @@ __global__ void packed_spectrum_product_kernel(const cplx<R>* __restrict__ Z, in
     }
 }
 
+// detector sampling (prysm/detector.py:151-338): block mean / sum over fy x fx samples, its adjoint (repeat), and the
+// analytic pixel / OLPF transfer functions on separable frequency vectors
+template <typename R>
+__global__ void bindown_kernel(const R* __restrict__ in, int oy, int ox, int fy, int fx, R scale, R* __restrict__ out) {
+    const long long n = (long long)oy * ox;
+    const long long in_ld = (long long)ox * fx;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / ox), x = (int)(i - (long long)y * ox);
+        const R* p = in + (long long)y * fy * in_ld + (long long)x * fx;
+        double acc = 0.0;
+        for (int a = 0; a < fy; ++a)
+            for (int b = 0; b < fx; ++b) acc += (double)p[a * in_ld + b];
+        out[i] = (R)(acc * (double)scale);
+    }
+}
+
+template <typename R>
+__global__ void tile_kernel(const R* __restrict__ in, int ny, int nx, int fy, int fx, R scale, R* __restrict__ out) {
+    const long long ox = (long long)nx * fx, n = (long long)ny * fy * ox;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long y = i / ox, x = i - y * ox;
+        out[i] = scale * in[(y / fy) * nx + x / fx];
+    }
+}
+
+// kind 0: sinc(fx wx) sinc(fy wy) (pixel_ft);  1: cos(2 wx fx) cos(2 wy fy) (olpf_ft)
+template <typename R>
+__global__ void separable_tf_kernel(int kind, const R* __restrict__ fxv, const R* __restrict__ fyv, int ny, int nx, double wx,
+                                    double wy, R* __restrict__ out) {
+    const long long n = (long long)ny * nx;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / nx), x = (int)(i - (long long)y * nx);
+        const double ax = (double)fxv[x] * wx, ay = (double)fyv[y] * wy;
+        double v;
+        if (kind == 0) v = (ax == 0.0 ? 1.0 : sinpi(ax) / (M_PI * ax)) * (ay == 0.0 ? 1.0 : sinpi(ay) / (M_PI * ay));
+        else v = cos(2.0 * ax) * cos(2.0 * ay);
+        out[i] = (R)v;
+    }
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -112,6 +152,42 @@ extern "C" int pb_packed_spectrum_product(pb_handle_t hh, int dtype, const void*
     const int g = grid_for((long long)ny * nx, 256, h->sm_count);
     if (dtype == PB_C64) packed_spectrum_product_kernel<float><<<g, 256, 0, st>>>((const float2*)Z, ny, nx, (float)scale, im_scale_dev, (float2*)out);
     else packed_spectrum_product_kernel<double><<<g, 256, 0, st>>>((const double2*)Z, ny, nx, scale, im_scale_dev, (double2*)out);
+    PB_LAUNCH_CHECK(h);
+    return PB_OK;
+}
+
+extern "C" int pb_bindown(pb_handle_t hh, int dtype, const void* in, int ny, int nx, int fy, int fx, int mean, void* out,
+                          void* stream) {
+    PB_HANDLE(hh);
+    if (!in || !out || fy < 1 || fx < 1 || ny < fy || nx < fx || ny % fy || nx % fx)
+        return fail(h, PB_ERR_INVALID, "array shape must be a positive integer multiple of the binning factor");
+    const int oy = ny / fy, ox = nx / fx;
+    const double scale = mean ? 1.0 / ((double)fy * fx) : 1.0;
+    const int g = grid_for((long long)oy * ox, 256, h->sm_count);
+    if (dtype == PB_C64) bindown_kernel<float><<<g, 256, 0, st>>>((const float*)in, oy, ox, fy, fx, (float)scale, (float*)out);
+    else bindown_kernel<double><<<g, 256, 0, st>>>((const double*)in, oy, ox, fy, fx, scale, (double*)out);
+    PB_LAUNCH_CHECK(h);
+    return PB_OK;
+}
+
+extern "C" int pb_tile(pb_handle_t hh, int dtype, const void* in, int ny, int nx, int fy, int fx, double scale, void* out,
+                       void* stream) {
+    PB_HANDLE(hh);
+    if (!in || !out || fy < 1 || fx < 1 || ny < 1 || nx < 1) return fail(h, PB_ERR_INVALID, "bad tile arguments");
+    const int g = grid_for((long long)ny * fy * nx * fx, 256, h->sm_count);
+    if (dtype == PB_C64) tile_kernel<float><<<g, 256, 0, st>>>((const float*)in, ny, nx, fy, fx, (float)scale, (float*)out);
+    else tile_kernel<double><<<g, 256, 0, st>>>((const double*)in, ny, nx, fy, fx, scale, (double*)out);
+    PB_LAUNCH_CHECK(h);
+    return PB_OK;
+}
+
+extern "C" int pb_separable_tf(pb_handle_t hh, int dtype, int kind, const void* fx, const void* fy, int ny, int nx, double wx,
+                               double wy, void* out, void* stream) {
+    PB_HANDLE(hh);
+    if (!fx || !fy || !out || ny < 1 || nx < 1 || kind < 0 || kind > 1) return fail(h, PB_ERR_INVALID, "bad transfer-function arguments");
+    const int g = grid_for((long long)ny * nx, 256, h->sm_count);
+    if (dtype == PB_C64) separable_tf_kernel<float><<<g, 256, 0, st>>>(kind, (const float*)fx, (const float*)fy, ny, nx, wx, wy, (float*)out);
+    else separable_tf_kernel<double><<<g, 256, 0, st>>>(kind, (const double*)fx, (const double*)fy, ny, nx, wx, wy, (double*)out);
     PB_LAUNCH_CHECK(h);
     return PB_OK;
 }

@@ -120,3 +120,30 @@ def test_fourier_resample(pb, gold, prec):
         fr(a, -1)
     with pytest.raises(ValueError):
         fr(a, 0.01)
+
+
+@pytest.mark.parametrize('prec', [64, 32])
+def test_detector_sampling(pb, gold, prec):
+    rdt, cdt, tol = setprec(pb, prec)
+    g = gold
+    D = pb.detector
+    ob = g['obj'].astype(rdt)
+    tol = 1e-14 if prec == 64 else 1e-6
+    for i, fac in enumerate((2, 3, (2, 3), (4, 6))):
+        assert rel_linf(host(D.bindown(ob, fac, 'avg')), g[f'bin{i}_avg']) < tol
+        assert rel_linf(host(D.bindown(ob, fac, 'sum')), g[f'bin{i}_sum']) < tol
+        assert rel_linf(host(D.tile(g['psf'][:6, :5].astype(rdt), fac, 'sum')), g[f'tile{i}_sum']) < tol
+    fx, fy = O.transfer_function_grids(g['obj'].shape, 2.0, False, rdt)[:2]
+    assert rel_linf(host(D.pixel_ft(fx, fy, 3.0, 2.5)), g['pixel_ft']) < tol * 5
+    assert rel_linf(host(D.olpf_ft(fx, fy, 0.7, 0.9)), g['olpf_ft']) < tol * 5
+    with pytest.raises(ValueError, match='mode must be average or sum'):
+        D.bindown(ob, 2, 'median')
+    with pytest.raises(ValueError):
+        D.bindown(ob, 5)                                   # 36 x 30 is not a multiple of 5 on both axes
+    with pytest.raises(ValueError, match='scaling must be average or sum'):
+        D.tile(ob, 2, 'max')
+    # the image chain end to end on the device: blur by pixel and OLPF transfer functions, bin to detector pixels
+    blurred = pb.convolution.apply_transfer_functions(ob, 2.0, [lambda fx, fy: D.pixel_ft(fx, fy, 3.0, 2.5),
+                                                                 lambda fx, fy: D.olpf_ft(fx, fy, 0.7, 0.9)])
+    ref = O.apply_transfer_functions(g['obj'], [g['pixel_ft'], g['olpf_ft']])
+    assert rel_linf(host(D.bindown(blurred, (2, 3))), O.bindown(ref, (2, 3))) < (1e-12 if prec == 64 else 3e-6)

@@ -49,3 +49,18 @@ def test_fourier_resample(gold):
     with pytest.raises(ValueError):
         O.fourier_resample(g['obj'], -1)
     assert np.allclose(O.fourier_resample(np.ones((8, 8)), (2, 3)), 1, atol=1e-12)      # tests/test_fttools.py:229-235
+
+
+def test_detector_sampling(gold):
+    g = gold
+    for i, fac in enumerate((2, 3, (2, 3), (4, 6))):
+        assert rel_linf(O.bindown(g['obj'], fac, 'avg'), g[f'bin{i}_avg']) < 1e-15
+        assert rel_linf(O.bindown(g['obj'], fac, 'sum'), g[f'bin{i}_sum']) < 1e-15
+        assert rel_linf(O.tile(g['psf'][:6, :5], fac, 'sum'), g[f'tile{i}_sum']) < 1e-15
+    fx, fy = O.transfer_function_grids(g['obj'].shape, 2.0, False)[:2]
+    assert rel_linf(O.pixel_ft(fx, fy, 3.0, 2.5), g['pixel_ft']) < 1e-15
+    assert rel_linf(O.olpf_ft(fx, fy, 0.7, 0.9), g['olpf_ft']) < 1e-15
+    a = np.arange(24.0).reshape(4, 6)
+    assert np.vdot(O.bindown(a, 2, 'sum'), np.ones((2, 3))) == np.vdot(a, O.tile(np.ones((2, 3)), 2, 'avg'))   # adjoint pair
+    with pytest.raises(ValueError):
+        O.bindown(a, 2, 'median')
