@@ -517,14 +517,14 @@ class Wavefront:
             data = psf_from_amp_and_phase(amp, opd, self.wavelength, Q, field=True)
         else:
             data = focus(self.data, Q=Q)
-        dx = pupil_sample_to_psf_sample(self.dx, data.shape[1], self.wavelength, efl)
+        dx = pupil_sample_to_psf_sample(self.dx, data.shape[-1], self.wavelength, efl)
         return Wavefront(data, self.wavelength, dx, space='psf')
 
     def focus_adjoint(self, efl, Q=2):
         """prysm/propagation/wavefront.py:506-532."""
         if self.space != 'psf':
             raise ValueError('can only apply adjoint from a psf to pupil plane')
-        samples = self.data.shape[1]
+        samples = self.data.shape[-1]
         data = focus_adjoint(self.data, Q=Q)
         dx = psf_sample_to_pupil_sample(self.dx, samples, self.wavelength, efl)
         return Wavefront(data, self.wavelength, dx, space='pupil')
@@ -534,14 +534,14 @@ class Wavefront:
         if self.space != 'psf':
             raise ValueError('can only propagate from a psf to pupil plane')
         data = unfocus(self.data, Q=Q)
-        dx = psf_sample_to_pupil_sample(self.dx, data.shape[1], self.wavelength, efl)
+        dx = psf_sample_to_pupil_sample(self.dx, data.shape[-1], self.wavelength, efl)
         return Wavefront(data, self.wavelength, dx, space='pupil')
 
     def unfocus_adjoint(self, efl, Q=2):
         """prysm/propagation/wavefront.py:562-588."""
         if self.space != 'pupil':
             raise ValueError('can only apply adjoint from a pupil to psf plane')
-        samples = self.data.shape[1]
+        samples = self.data.shape[-1]
         data = unfocus_adjoint(self.data, Q=Q)
         dx = pupil_sample_to_psf_sample(self.dx, samples, self.wavelength, efl)
         return Wavefront(data, self.wavelength, dx, space='psf')

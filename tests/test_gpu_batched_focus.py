@@ -63,3 +63,16 @@ def test_batched_phase_screen_input_shared_amplitude(pb):
     amps = torch.stack([amp, ~amp, amp])
     got2 = _ops.fft2_batch(None, (2 * n, 2 * n), dir=-1, scale=1.0 / (2 * n), shift_in=True, shift_out=True, amp=amps, opd=opd, kscale=k)
     assert torch.equal(got2[1], pb.propagation.psf_from_amp_and_phase(~amp, opd[1], 0.6328, 2, field=True))
+
+
+def test_wavefront_focus_on_a_stack(pb):
+    """Wavefront.focus / unfocus accept a (B, N, N) stack: sample spacing from the last axis, fields batched."""
+    P = pb.propagation
+    w = crand((3, 512, 512), 11)
+    wf = P.Wavefront(w, 0.6328, 10.0 / 512)
+    psf = wf.focus(100.0, Q=2)
+    one = P.Wavefront(w[1], 0.6328, 10.0 / 512).focus(100.0, Q=2)
+    assert psf.dx == one.dx and psf.space == 'psf' and tuple(psf.data.shape) == (3, 1024, 1024)
+    assert torch.equal(psf.data[1], one.data)
+    back = psf.unfocus(100.0, Q=1)
+    assert back.dx == pytest.approx(wf.dx / 2) and tuple(back.data.shape) == (3, 1024, 1024)
