@@ -75,4 +75,4 @@ def test_wavefront_focus_on_a_stack(pb):
     assert psf.dx == one.dx and psf.space == 'psf' and tuple(psf.data.shape) == (3, 1024, 1024)
     assert torch.equal(psf.data[1], one.data)
     back = psf.unfocus(100.0, Q=1)
-    assert back.dx == pytest.approx(wf.dx / 2) and tuple(back.data.shape) == (3, 1024, 1024)
+    assert back.dx == pytest.approx(wf.dx) and tuple(back.data.shape) == (3, 1024, 1024)
