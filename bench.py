@@ -165,6 +165,35 @@ def measure_mdft_c3(pb, peaks):
                          'note': 'algorithmic flops vs the bf16 peak; the path issues 3 TF32 MMAs per product (TF32 runs at half the bf16 rate)'}}
 
 
+def measure_fused_psf(stack, peak):
+    """SURVEY 8(d) 'fused PSF variant': unit = focus(...).intensity with |.|^2 formed in the last pass (fp32 out).
+    Algorithmic bytes 8*N^2 + 4*K^2 = 100 663 296 per PSF."""
+    import torch
+    from prysm_b200 import _ops
+    from prysm_b200._capi import OUT_INTENSITY
+    nb = stack.shape[0]
+    out = torch.empty((nb, K, K), dtype=torch.float32, device=stack.device)
+
+    def step():
+        _ops.fft2_batch(stack, (K, K), dir=-1, scale=1.0 / K, shift_in=True, shift_out=True, out_kind=OUT_INTENSITY, out=out)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / (reps * nb)
+    alg = 8 * N * N + 4 * K * K
+    return {'workload': 'C2 fused PSF variant: 2048x2048 complex64 pupil -> |focus(Q=2)|^2 4096x4096 float32, batched',
+            'us_per_psf': sec * 1e6, 'psf_per_s': 1.0 / sec,
+            'roofline': {'bound': 'hbm', 'achieved': alg / sec / 1e9, 'peak': peak, 'unit': 'GB/s',
+                         'frac': alg / sec / 1e9 / peak, 'traffic': None, 'algorithmic_bytes_per_psf': alg}}
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm (oracle port: numpy + scipy.fft pocketfft, the same
     third-party FFT the reference calls) on this box's host cores, all threads, same config/metric."""
@@ -338,6 +367,10 @@ def run_b200(args):
             line['cpu_baseline'] = cpu
         if world == 1:
             line['mdft_c3'] = measure_mdft_c3(pb, peaks)
+            try:
+                line['fused_psf'] = measure_fused_psf(stack, peak)
+            except Exception as exc:  # an extra: never take the headline line down with it
+                line['fused_psf'] = {'error': repr(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -86,6 +86,12 @@ def focus_intensity(wavefunction, Q, weight=1.0, out=None):
     written).  With `out`, accumulates out += weight*|.|^2 -- the per-wavelength term of the
     incoherent sum (prysm/propagation/wavefront.py:147-151, prysm/polynomials/fitting.py:37)."""
     w = _field(wavefunction)
+    if w.ndim == 3:      # a stack of independent fields -> a stack of PSFs in one batched call (no accumulate form)
+        if out is not None or weight != 1.0:
+            raise ValueError('the batched form writes one |.|^2 plane per field: weight / out are for single fields')
+        ky, kx = _padded_shape(w.shape[1:], Q)
+        return _ops.fft2_batch(w, (ky, kx), dir=-1, scale=1.0 / math.sqrt(ky * kx), shift_in=True, shift_out=True,
+                               out_kind=OUT_INTENSITY)
     ky, kx = _padded_shape(w.shape, Q)
     kind = OUT_INTENSITY if out is None else OUT_ACCUMULATE
     return _ops.fft2(w, (ky, kx), dir=-1, scale=1.0 / math.sqrt(ky * kx), shift_in=True, shift_out=True,

@@ -76,3 +76,14 @@ def test_wavefront_focus_on_a_stack(pb):
     assert torch.equal(psf.data[1], one.data)
     back = psf.unfocus(100.0, Q=1)
     assert back.dx == pytest.approx(wf.dx) and tuple(back.data.shape) == (3, 1024, 1024)
+
+
+def test_batched_fused_intensity(pb):
+    P = pb.propagation
+    w = crand((5, 512, 512), 21)
+    got = P.focus_intensity(w, 2)
+    assert got.dtype == torch.float32 and tuple(got.shape) == (5, 1024, 1024)
+    for b in (0, 4):
+        assert torch.equal(got[b], P.focus_intensity(w[b], 2))
+    with pytest.raises(ValueError):
+        P.focus_intensity(w, 2, weight=0.5)
