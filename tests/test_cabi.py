@@ -51,3 +51,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert 'prysm_oracle' not in txt and 'import oracle' not in txt, f
+
+
+def test_python_constants_match_the_header_enums():
+    """The integer codes the ctypes layer passes are the enum values the header declares."""
+    from prysm_b200 import _capi
+    src = open(os.path.join(ROOT, 'include', 'prysm_b200.h')).read()
+    enums = {k: int(v) for k, v in re.findall(r'\b(PB_[A-Z0-9_]+)\s*=\s*(-?\d+)', src)}
+    pairs = {'PB_C64': _capi.PB_C64, 'PB_C128': _capi.PB_C128, 'PB_IN_COMPLEX': _capi.IN_COMPLEX, 'PB_IN_REAL': _capi.IN_REAL,
+             'PB_IN_AMP_OPD': _capi.IN_AMP_OPD, 'PB_AMP_NONE': _capi.AMP_NONE, 'PB_AMP_REAL': _capi.AMP_REAL,
+             'PB_AMP_U8': _capi.AMP_U8, 'PB_OUT_COMPLEX': _capi.OUT_COMPLEX, 'PB_OUT_INTENSITY': _capi.OUT_INTENSITY,
+             'PB_OUT_ACCUMULATE': _capi.OUT_ACCUMULATE, 'PB_MASK_REAL': _capi.MASK_REAL, 'PB_MASK_COMPLEX': _capi.MASK_COMPLEX,
+             'PB_MASK_CONJ': _capi.MASK_CONJ, 'PB_MASK_ONE_MINUS': _capi.MASK_ONE_MINUS, 'PB_MASK_REAL_OUT': _capi.MASK_REAL_OUT,
+             'PB_MASK_ACCUMULATE': _capi.MASK_ACCUMULATE}
+    for name, val in pairs.items():
+        assert enums[name] == val, name
+    assert enums['PB_OK'] == 0 and enums['PB_ERR_INVALID'] == -1      # Handle.check maps -1 to ValueError
+
+
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing outside tests/, bench.py and __graft_entry__.py may import it."""
+    allowed = {os.path.join(ROOT, 'bench.py'), os.path.join(ROOT, '__graft_entry__.py')}
+    for dirpath, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in ('.git', 'tests', 'oracle', 'gpurun_out', 'baseline', '__pycache__', '.pytest_cache')]
+        for f in files:
+            path = os.path.join(dirpath, f)
+            if f.endswith('.py') and path not in allowed:
+                assert 'prysm_oracle' not in open(path).read(), path
