@@ -162,6 +162,38 @@ def full():
     print('full_c3.npz written')
 
 
+def full_c45():
+    """BASELINE configs C4 (2048^2 x wavelengths, CZT -> 2048^2) and C5 (4096^2 free-space plane with a phase screen):
+    windows / strided samples / sums of the reference's fp64 outputs -> full_c4.npz, full_c5.npz."""
+    N = M = 2048
+    amp, opd, dx = ref_pupil(N)
+    g = dict(N=np.int64(N), M=np.int64(M), focal_dx=np.float64(2.5), efl=np.float64(100.0))
+    tot = 0
+    for w, wt in ((0.5, 0.25), (0.7, 0.75)):
+        wf = Wavefront.from_amp_and_phase(amp, opd, w, dx)
+        ex = wf.prepare_executor(100.0, 2.5, M, kind='czt')
+        f = wf.focus_dft(ex).data
+        I = np.abs(f) ** 2
+        tot = tot + wt * I
+        tag = f'w{int(w * 10)}_'
+        g.update({tag + 'field_win': window(f, 64), tag + 'field_stride': f[::64, ::64], tag + 'absmax': np.float64(np.abs(f).max()),
+                  tag + 'I_sum': np.float64(I.sum())})
+    g.update(sum_win=window(tot, 64), sum_stride=tot[::64, ::64], sum_max=np.float64(tot.max()), sum_total=np.float64(tot.sum()))
+    np.savez_compressed(os.path.join(OUT, 'full_c4.npz'), **g)
+    print('full_c4.npz written')
+    N = 4096
+    amp, opd, dx = ref_pupil(N)
+    wf = Wavefront.from_amp_and_phase(amp, opd, HeNe, dx)
+    phi = np.random.default_rng(1000).normal(0, 0.1, (N, N))
+    scr = Wavefront(np.exp(1j * phi), HeNe, dx)
+    out = (wf * scr).free_space(dz=5.0, Q=1).data
+    g = dict(N=np.int64(N), dz=np.float64(5.0), field_win=window(out, 64), field_stride=out[::128, ::128],
+             absmax=np.float64(np.abs(out).max()), E_out=np.float64((np.abs(out) ** 2).sum()),
+             E_in=np.float64((np.abs(wf.data) ** 2).sum()), edge=out[N // 2, 1000:1100])
+    np.savez_compressed(os.path.join(OUT, 'full_c5.npz'), **g)
+    print('full_c5.npz written')
+
+
 def coronagraph():
     """Adjoint twins + Lyot-coronagraph compositions -> coronagraph.npz."""
     from prysm.polynomials import sum_of_2d_modes_adjoint
@@ -318,7 +350,7 @@ def imagechain():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['small', 'full', 'coronagraph', 'synthesis', 'imagechain']   # name the fixtures to (re)write
+    which = sys.argv[1:] or ['small', 'full', 'full_c45', 'coronagraph', 'synthesis', 'imagechain']   # name the fixtures to (re)write
     for name in which:
-        {'small': small, 'full': full, 'coronagraph': coronagraph, 'synthesis': synthesis,
+        {'small': small, 'full': full, 'full_c45': full_c45, 'coronagraph': coronagraph, 'synthesis': synthesis,
          'imagechain': imagechain}[name]()

@@ -1,0 +1,74 @@
+"""GPU: BASELINE configs C4 and C5 at FULL size against the reference's own fp64 outputs (tests/golden/full_c4.npz,
+full_c5.npz: windows, strided samples, sums written by oracle/make_golden.py full_c45), complex64 path.
+
+  C4  2048^2 pupil -> CZT -> 2048^2 field at two wavelengths, weighted incoherent sum (polychromatic_psf)
+  C5  4096^2 field x unit-modulus phase screen -> free_space(dz = 5 mm)
+
+Tolerance: relative L-inf (normalised by the reference's max) 2e-6 for the CZT fields (fp32 Bluestein),
+3e-6 for the free-space plane (three fp32 transforms), sums 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+import prysm_oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+HeNe = 0.6328
+
+
+@pytest.fixture(scope='module')
+def pb():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    import prysm_b200
+    prysm_b200.config.precision = 32
+    yield prysm_b200
+    prysm_b200.config.precision = 64
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def test_c4_czt_fields_and_incoherent_sum_vs_reference(pb):
+    g = load_golden('full_c4.npz')
+    P = pb.propagation
+    N = M = 2048
+    amp, opd, dx = O.synthetic_pupil(N, np.float32)
+    cy = M // 2
+    for w in (0.5, 0.7):
+        tag = f'w{int(w * 10)}_'
+        wf = P.Wavefront.from_amp_and_phase(amp, opd, w, dx)
+        f = host(wf.focus_dft(wf.prepare_executor(100.0, 2.5, M, kind='czt')).data)
+        den = float(g[tag + 'absmax'])
+        assert f.shape == (M, M)
+        assert np.abs(f[::64, ::64] - g[tag + 'field_stride']).max() / den < 2e-6
+        assert np.abs(f[cy - 32:cy + 32, cy - 32:cy + 32] - g[tag + 'field_win']).max() / den < 2e-6
+        I = (f.real.astype(np.float64) ** 2 + f.imag.astype(np.float64) ** 2).sum()
+        assert I == pytest.approx(float(g[tag + 'I_sum']), rel=1e-5)
+    from prysm_b200.polychromatic import polychromatic_psf
+    tot = host(polychromatic_psf(amp, opd, [0.5, 0.7], [0.25, 0.75], dx, 100.0, 2.5, M, kind='czt')).astype(np.float64)
+    smax = float(g['sum_max'])
+    assert np.abs(tot[::64, ::64] - g['sum_stride']).max() / smax < 2e-6
+    assert np.abs(tot[cy - 32:cy + 32, cy - 32:cy + 32] - g['sum_win']).max() / smax < 2e-6
+    assert tot.sum() == pytest.approx(float(g['sum_total']), rel=1e-5)
+
+
+def test_c5_screen_and_free_space_plane_vs_reference(pb):
+    g = load_golden('full_c5.npz')
+    P = pb.propagation
+    N = 4096
+    amp, opd, dx = O.synthetic_pupil(N, np.float32)
+    wf = P.Wavefront.from_amp_and_phase(amp, opd, HeNe, dx)
+    phi = np.random.default_rng(1000).normal(0, 0.1, (N, N)).astype(np.float32)
+    scr = P.Wavefront.phase_screen(phi * (HeNe * 1e3 / (2 * np.pi)), HeNe, dx)       # exp(i*phi): OPD[nm] = phi*wvl/(2 pi)
+    out = host((wf * scr).free_space(dz=float(g['dz']), Q=1).data)
+    den = float(g['absmax'])
+    c = N // 2
+    assert out.shape == (N, N)
+    assert np.abs(out[::128, ::128] - g['field_stride']).max() / den < 3e-6
+    assert np.abs(out[c - 32:c + 32, c - 32:c + 32] - g['field_win']).max() / den < 3e-6
+    assert np.abs(out[c, 1000:1100] - g['edge']).max() / den < 3e-6
+    E = (out.real.astype(np.float64) ** 2 + out.imag.astype(np.float64) ** 2).sum()
+    assert E == pytest.approx(float(g['E_out']), rel=1e-5)

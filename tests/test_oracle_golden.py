@@ -103,3 +103,38 @@ def test_c1_full_reference_window():
     I = O.intensity(psf)
     assert I.sum() == pytest.approx(float(g['I_sum']), rel=1e-10)
     assert I.sum() == pytest.approx(float(g['E_in']), rel=1e-12)  # ortho FFT conserves energy
+
+
+def test_c4_full_reference_samples():
+    """BASELINE config C4 (2048^2 -> 2048^2 CZT per wavelength, weighted incoherent sum) against the reference's stored
+    fp64 samples at two wavelengths."""
+    g = load_golden('full_c4.npz')
+    amp, opd, dx = O.synthetic_pupil(2048, np.float64)
+    tot = 0
+    for w, wt in ((0.5, 0.25), (0.7, 0.75)):
+        ex = O.prepare_executor(dx, (2048, 2048), 2.5, (2048, 2048), w, 100.0, kind='czt')
+        f = ex(O.from_amp_and_phase(amp, opd, w))
+        tag = f'w{int(w * 10)}_'
+        assert np.abs(f[::64, ::64] - g[tag + 'field_stride']).max() / float(g[tag + 'absmax']) < 1e-9
+        cy = 1024
+        assert np.abs(f[cy - 32:cy + 32, cy - 32:cy + 32] - g[tag + 'field_win']).max() / float(g[tag + 'absmax']) < 1e-9
+        I = O.intensity(f)
+        assert I.sum() == pytest.approx(float(g[tag + 'I_sum']), rel=1e-9)
+        tot = tot + wt * I
+    assert np.abs(tot[::64, ::64] - g['sum_stride']).max() / float(g['sum_max']) < 1e-9
+    assert tot.sum() == pytest.approx(float(g['sum_total']), rel=1e-9)
+
+
+def test_c5_full_reference_samples():
+    """BASELINE config C5: one 4096^2 plane -- screen multiply then free_space(dz = 5 mm) -- against the reference."""
+    g = load_golden('full_c5.npz')
+    amp, opd, dx = O.synthetic_pupil(4096, np.float64)
+    field = O.from_amp_and_phase(amp, opd, HeNe)
+    phi = np.random.default_rng(1000).normal(0, 0.1, (4096, 4096))
+    out = O.angular_spectrum(field * np.exp(1j * phi), HeNe, dx, 5.0, 1)
+    den = float(g['absmax'])
+    assert np.abs(out[::128, ::128] - g['field_stride']).max() / den < 1e-9
+    assert np.abs(out[2048 - 32:2048 + 32, 2048 - 32:2048 + 32] - g['field_win']).max() / den < 1e-9
+    assert np.abs(out[2048, 1000:1100] - g['edge']).max() / den < 1e-9
+    assert (np.abs(out) ** 2).sum() == pytest.approx(float(g['E_out']), rel=1e-10)
+    assert float(g['E_out']) == pytest.approx(float(g['E_in']), rel=1e-10)        # |TF| = 1, |screen| = 1
