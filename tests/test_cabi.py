@@ -78,3 +78,26 @@ def test_only_tests_smoke_and_bench_touch_the_oracle():
             path = os.path.join(dirpath, f)
             if f.endswith('.py') and path not in allowed:
                 assert 'prysm_oracle' not in open(path).read(), path
+
+
+def test_header_is_valid_c99_and_the_c_example_links():
+    """The boundary is a C ABI: the header must compile as plain C (not only as C++), and the example that calls it
+    from C must link against the built library."""
+    import shutil
+    import subprocess
+    import tempfile
+    from prysm_b200 import _capi
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc on this box')
+    src = os.path.join(ROOT, 'examples', 'focus_from_c.c')
+    inc = os.path.join(ROOT, 'include')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', inc, '-fsyntax-only', src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cudart = '/usr/local/cuda/lib64'
+    if os.path.isdir(cudart):
+        with tempfile.TemporaryDirectory() as d:
+            r = subprocess.run([gcc, '-std=c99', '-I', inc, src, '-L', os.path.dirname(_capi.LIB_PATH), '-lprysm_b200',
+                                '-L', cudart, '-lcudart', '-o', os.path.join(d, 'focus_from_c')], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
