@@ -101,3 +101,26 @@ def test_header_is_valid_c99_and_the_c_example_links():
             r = subprocess.run([gcc, '-std=c99', '-I', inc, src, '-L', os.path.dirname(_capi.LIB_PATH), '-lprysm_b200',
                                 '-L', cudart, '-lcudart', '-o', os.path.join(d, 'focus_from_c')], capture_output=True, text=True)
             assert r.returncode == 0, r.stderr
+
+
+def test_every_entry_point_rejects_a_null_handle():
+    """No entry point may dereference a NULL handle: each returns PB_ERR_INVALID (-1) instead (nothing crosses the
+    boundary as a crash).  Needs no GPU -- the check is the first thing every call does."""
+    from prysm_b200 import _capi
+    no_handle = {'pb_create', 'pb_destroy', 'pb_last_error', 'pb_version', 'pb_launch_count', 'pb_mdft_work_elems',
+                 'pb_mdft_tc_supported', 'pb_mdft_tc_work_bytes'}
+    checked = 0
+    for name, (_, args) in _capi.SIGNATURES.items():
+        if name in no_handle:
+            continue
+        vals = []
+        for a in args:
+            if a in (ctypes.c_int, ctypes.c_longlong):
+                vals.append(0)
+            elif a is ctypes.c_double:
+                vals.append(0.0)
+            else:
+                vals.append(None)       # pointers, including the handle
+        assert getattr(_capi.lib, name)(*vals) == -1, name
+        checked += 1
+    assert checked == len(_capi.SIGNATURES) - len(no_handle)
