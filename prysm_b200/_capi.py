@@ -133,17 +133,39 @@ class Handle:
             pass
 
 
-_handles = {}
+_handles = {}          # (device, raw stream pointer) -> Handle, in least-recently-used order
+_pinned = set()        # keys whose handle must outlive the cache (a captured CUDA graph replays into its scratch)
+MAX_HANDLES_PER_DEVICE = 8
 
 
 def handle_for(device_index, stream=0):
     """One handle per (device, stream): a handle's scratch arenas are only ordered by the stream its calls run
-    on, so work issued on different streams must not share one (include/prysm_b200.h: 'not thread-safe')."""
+    on, so work issued on different streams must not share one (include/prysm_b200.h: 'not thread-safe').
+    The cache is bounded: beyond MAX_HANDLES_PER_DEVICE the least recently used un-pinned handle of that device is
+    destroyed (pb_destroy synchronises the device first), so short-lived side streams do not accumulate twiddle
+    tables and scratch arenas that torch's allocator cannot see."""
     key = (device_index, stream)
-    h = _handles.get(key)
+    h = _handles.pop(key, None)
     if h is None:
-        h = _handles[key] = Handle(device_index)
+        mine = [k for k in _handles if k[0] == device_index and k not in _pinned]
+        while len(mine) >= MAX_HANDLES_PER_DEVICE:
+            _handles.pop(mine.pop(0)).close()
+        h = Handle(device_index)
+    _handles[key] = h          # (re)insert as most recently used
     return h
+
+
+def pin_handle(device_index, stream):
+    """Keep the handle of (device, stream) alive for the life of the process (graphs.capture)."""
+    _pinned.add((device_index, stream))
+
+
+def release_handle(device_index, stream):
+    """Destroy the handle of (device, stream) now (explicit close of a side stream's engine state)."""
+    _pinned.discard((device_index, stream))
+    h = _handles.pop((device_index, stream), None)
+    if h is not None:
+        h.close()
 
 
 def launch_count(device_index):

@@ -76,6 +76,22 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _check_out(out, shape, dtype, device, name='out'):
+    """A caller-supplied output goes to the kernel as a raw pointer + row pitch: refuse anything the kernel would
+    misread (wrong dtype / shape / device, rows that are not unit-stride) instead of writing out of bounds."""
+    if not isinstance(out, torch.Tensor):
+        raise TypeError(f'`{name}` must be a torch.Tensor, got {type(out).__name__}')
+    if out.dtype != dtype:
+        raise ValueError(f'`{name}` has dtype {out.dtype}, the operation writes {dtype}')
+    if tuple(out.shape) != tuple(shape):
+        raise ValueError(f'`{name}` has shape {tuple(out.shape)}, the operation writes {tuple(shape)}')
+    if out.device != device:
+        raise ValueError(f'`{name}` is on {out.device}, the input is on {device}')
+    if out.ndim and out.stride(-1) != 1:
+        raise ValueError(f'`{name}` must have unit stride along its last axis')
+    return out
+
+
 def _darr(v):
     v = np.ascontiguousarray(v, dtype=np.float64)
     return v, v.ctypes.data_as(C.POINTER(C.c_double))
@@ -108,11 +124,13 @@ def fft2(field, k=None, *, dir=-1, scale=1.0, shift_in=False, shift_out=False, c
     ny, nx = src.shape
     ky, kx = (ny, nx) if k is None else k
     oy, ox = (ky, kx) if crop is None else crop
+    odt = cdtype if out_kind == capi.OUT_COMPLEX else _REAL_OF[cdtype]
     if out is None:
-        odt = cdtype if out_kind == capi.OUT_COMPLEX else _REAL_OF[cdtype]
         if out_kind == capi.OUT_ACCUMULATE:
             raise ValueError('accumulate needs an existing `out` array')
         out = torch.empty((oy, ox), dtype=odt, device=src.device)
+    else:
+        _check_out(out, (oy, ox), odt, src.device)
     h, st = _ctx(src)
     h.check(lib.pb_fft2(h.ptr, _CODE[cdtype], _p(src), in_kind, _p(amp_t), amp_kind, float(kscale),
                         ny, nx, nx, ky, kx, int(dir), float(scale), int(shift_in), int(shift_out),
@@ -145,9 +163,13 @@ def fft2_batch(fields, k=None, *, dir=-1, scale=1.0, shift_in=False, shift_out=F
     src = src.contiguous()
     nb, ny, nx = src.shape
     ky, kx = (ny, nx) if k is None else k
+    odt = cdtype if out_kind == capi.OUT_COMPLEX else _REAL_OF[cdtype]
     if out is None:
-        odt = cdtype if out_kind == capi.OUT_COMPLEX else _REAL_OF[cdtype]
         out = torch.empty((nb, ky, kx), dtype=odt, device=src.device)
+    else:
+        _check_out(out, (nb, ky, kx), odt, src.device)
+        if out.stride(1) < kx or (nb > 1 and out.stride(0) < (ky - 1) * out.stride(1) + kx):
+            raise ValueError('`out` rows / fields overlap')
     h, st = _ctx(src)
     h.check(lib.pb_fft2_batch(h.ptr, _CODE[cdtype], _p(src), in_kind, _p(amp_t), amp_kind, float(kscale), nb,
                               src.stride(0), amp_bs, ny, nx, src.stride(1), ky, kx, int(dir), float(scale), int(shift_in),
@@ -329,6 +351,10 @@ def intensity(field, weight=1.0, out=None):
     acc = out is not None
     if out is None:
         out = torch.empty(field.shape, dtype=_REAL_OF[field.dtype], device=field.device)
+    else:
+        _check_out(out, field.shape, _REAL_OF[field.dtype], field.device)
+        if not out.is_contiguous():
+            raise ValueError('`out` must be contiguous')
     h, st = _ctx(field)
     h.check(lib.pb_intensity(h.ptr, _CODE[field.dtype], _p(field), field.numel(), float(weight), int(acc), _p(out), st))
     return out
@@ -361,6 +387,8 @@ def mul_outer(a, vy=None, vx=None, conj_y=False, conj_x=False, scale=1.0, out=No
     ny, nx = a.shape
     if out is None:
         out = torch.empty((ny, nx), dtype=a.dtype, device=a.device)
+    else:
+        _check_out(out, (ny, nx), a.dtype, a.device)
     h, st = _ctx(a)
     h.check(lib.pb_mul_outer(h.ptr, _CODE[a.dtype], _p(a), a.stride(0), ny, nx, _p(vy), int(conj_y), _p(vx),
                              int(conj_x), float(scale), _p(out), out.stride(0), st))
@@ -435,6 +463,9 @@ def mask_multiply(a, m=None, *, b=None, w=None, conj=False, one_minus=False, rea
     if out is None:
         out = torch.empty(a.shape, dtype=rd if real_out else a.dtype, device=a.device)
     else:
+        _check_out(out, a.shape, rd if real_out else a.dtype, a.device)
+        if not out.is_contiguous():
+            raise ValueError('`out` must be contiguous')
         flags |= capi.MASK_ACCUMULATE
     h, st = _ctx(a)
     h.check(lib.pb_mask_multiply(h.ptr, _CODE[a.dtype], _p(a), _p(b), _p(m), kind, flags, _p(w), float(scale),

@@ -266,8 +266,7 @@ __global__ void radial_window_kernel(int ny, int nx, double fdx, double shift, d
 using namespace pb;
 
 #define PB_HANDLE(hh)                                   \
-    Handle* h = reinterpret_cast<Handle*>(hh);          \
-    if (!h) return PB_ERR_INVALID;                      \
+    PB_ENTER(hh);                      \
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128"); \
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
 

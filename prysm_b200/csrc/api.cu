@@ -32,7 +32,10 @@ extern "C" int pb_create(pb_handle_t* out, int device) {
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return PB_ERR_CUDA;
-    if (cudaSetDevice(device) != cudaSuccess) return PB_ERR_CUDA;
+    DeviceGuard guard(device);   // the caller's current device is restored on return
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) return PB_ERR_CUDA;
+    if (cudaFree(0) != cudaSuccess) return PB_ERR_CUDA;   // make sure the device's primary context exists
     Handle* h = new Handle();
     h->device = device;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -44,7 +47,7 @@ extern "C" int pb_create(pb_handle_t* out, int device) {
 extern "C" int pb_destroy(pb_handle_t hh) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     if (!h) return PB_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     for (auto& kv : h->tables) cudaFree(kv.second);
     for (int i = 0; i < 3; ++i) if (h->scratch[i]) cudaFree(h->scratch[i]);

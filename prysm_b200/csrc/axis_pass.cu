@@ -160,12 +160,8 @@ static int launch_generic(Handle* h, const AxisPass& p, cudaStream_t st) {
     const size_t smem = (size_t)T * L * elem;
     int threads = (int)std::min<long long>(512, std::max<long long>(32, ((long long)T * L / 4 + 31) / 32 * 32));
     if (smem > 48 * 1024) {
-        static size_t set_f = 0, set_d = 0;
-        size_t& cur = std::is_same<R, float>::value ? set_f : set_d;
-        if (smem > cur) {
+        if (attr_needed(h, reinterpret_cast<const void*>(axis_pass_kernel<R>)))
             PB_CUDA(h, cudaFuncSetAttribute(axis_pass_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-            cur = cap;
-        }
     }
     const void* tw = nullptr;
     PB_TRY(get_twiddles(h, L, p.dtype, &tw));

@@ -126,8 +126,7 @@ using namespace pb;
 
 extern "C" int pb_cgemm(pb_handle_t hh, int dtype, int opA, int opB, int m, int n, int k, double alpha, const void* A,
                         long long lda, const void* B, long long ldb, void* C, long long ldc, void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (m < 1 || n < 1 || k < 1 || opA < 0 || opA > 3 || opB < 0 || opB > 3) return fail(h, PB_ERR_INVALID, "bad gemm arguments");
     return cgemm_simt(h, dtype, opA, opB, m, n, k, alpha, A, lda, B, ldb, C, ldc, reinterpret_cast<cudaStream_t>(stream));
@@ -141,13 +140,10 @@ extern "C" long long pb_mdft_work_elems(int my, int ny, int mx, int nx, int adjo
 extern "C" int pb_mdft_apply(pb_handle_t hh, int dtype, const void* Ey, const void* Ex, int my, int ny, int mx, int nx,
                              const void* a, void* out, double norm, int adjoint, int left_first, void* work,
                              void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (my < 1 || ny < 1 || mx < 1 || nx < 1 || !Ey || !Ex || !a || !out || !work) return fail(h, PB_ERR_INVALID, "bad mdft arguments");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int rc = try_mdft_tc(h, dtype, Ey, Ex, my, ny, mx, nx, a, out, norm, adjoint, left_first, work, st);
-    if (rc != PB_ERR_UNSUPPORTED) return rc;
     if (!adjoint) {
         if (left_first) {  // (Ey @ a) @ Ex^T
             PB_TRY(cgemm_simt(h, dtype, 0, 0, my, nx, ny, 1.0, Ey, ny, a, nx, work, nx, st));

@@ -1,10 +1,13 @@
 // Shared declarations for libprysm_b200: handle, error plumbing, complex helpers.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <complex>
 #include <cstdio>
 #include <map>
+#include <set>
 #include <string>
 #include <type_traits>
 #include <utility>
@@ -51,6 +54,19 @@ struct TwKey {
     }
 };
 
+// cache key of a TMA descriptor: everything cuTensorMapEncodeTiled was given
+struct MapKey {
+    const void* base; int kind; long long a, b, c, d;
+    bool operator<(const MapKey& o) const {
+        if (base != o.base) return base < o.base;
+        if (kind != o.kind) return kind < o.kind;
+        if (a != o.a) return a < o.a;
+        if (b != o.b) return b < o.b;
+        if (c != o.c) return c < o.c;
+        return d < o.d;
+    }
+};
+
 struct Handle {
     int device = 0;
     std::string err;
@@ -61,7 +77,42 @@ struct Handle {
     size_t scratch_bytes[3] = {0, 0, 0};
     int sm_count = 148;
     int max_smem_optin = 0;
+    // kernels whose opt-in attributes (dynamic shared memory, carve-out) were set on THIS handle's device.
+    // cudaFuncSetAttribute acts on the current device's copy of the function, so the record is per handle
+    // (= per device and stream), never a process-wide static.
+    std::set<const void*> attr_done;
+    std::map<MapKey, CUtensorMap> maps;   // TMA descriptors by (base pointer, geometry)
 };
+
+// Makes the handle's device current for the duration of an entry point and restores the caller's device on
+// the way out (one process may drive several GPUs; torch's current device must not change under the caller).
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(int want) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != want) switched = cudaSetDevice(want) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// NVTX range per C-ABI call: shows up in nsys / ncu --nvtx timelines, a no-op without a tool attached
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
+// First lines of every extern "C" entry point that takes a handle
+#define PB_ENTER(hh)                                         \
+    pb::Handle* h = reinterpret_cast<pb::Handle*>(hh);       \
+    if (!h) return PB_ERR_INVALID;                           \
+    pb::DeviceGuard pb_guard_(h->device);                    \
+    pb::NvtxRange pb_range_(__func__)
+
+// true the first time a kernel is seen on this handle: the caller then sets its opt-in attributes
+inline bool attr_needed(Handle* h, const void* fn) { return h->attr_done.insert(fn).second; }
 
 inline int fail(Handle* h, int code, const std::string& msg) {
     if (h) h->err = msg;

@@ -219,8 +219,7 @@ __global__ void mdft_basis_kernel(const double* __restrict__ f, int m, const dou
 using namespace pb;
 
 #define PB_HANDLE(hh)                                   \
-    Handle* h = reinterpret_cast<Handle*>(hh);          \
-    if (!h) return PB_ERR_INVALID;                      \
+    PB_ENTER(hh);                      \
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128"); \
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
 

@@ -187,8 +187,7 @@ extern "C" int pb_fft2(pb_handle_t hh, int dtype, const void* in, int in_kind, c
                        double kscale, int ny, int nx, long long in_ld, int ky, int kx, int dir, double scale,
                        int shift_in, int shift_out, void* out, int out_kind, double weight, int oy, int ox,
                        long long out_ld, void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (ny < 1 || nx < 1 || ky < ny || kx < nx) return fail(h, PB_ERR_INVALID, "need 1 <= n <= k on both axes");
     if (oy < 1 || ox < 1 || oy > ky || ox > kx) return fail(h, PB_ERR_INVALID, "crop window must fit the transform");
@@ -210,8 +209,7 @@ extern "C" int pb_fft2_batch(pb_handle_t hh, int dtype, const void* in, int in_k
                              double kscale, int batch, long long in_bs, long long amp_bs, int ny, int nx, long long in_ld,
                              int ky, int kx, int dir, double scale, int shift_in, int shift_out, void* out, int out_kind,
                              double weight, int oy, int ox, long long out_ld, long long out_bs, void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (batch < 1) return fail(h, PB_ERR_INVALID, "batch must be >= 1");
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (ny < 1 || nx < 1 || ky < ny || kx < nx) return fail(h, PB_ERR_INVALID, "need 1 <= n <= k on both axes");
@@ -244,8 +242,7 @@ extern "C" int pb_fft2_batch(pb_handle_t hh, int dtype, const void* in, int in_k
 
 extern "C" int pb_fft1(pb_handle_t hh, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int n,
                        int dir, double scale, void* out, long long out_ld, void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (ny < 1 || nx < 1 || n < 1 || (axis != 0 && axis != 1)) return fail(h, PB_ERR_INVALID, "bad shape / axis");
     if (dir != -1 && dir != 1) return fail(h, PB_ERR_INVALID, "dir must be -1 or +1");
@@ -267,8 +264,7 @@ extern "C" int pb_axis_dft(pb_handle_t hh, int dtype, const void* in, int ny, in
                            int dir, double scale, const void* pre_e, int pre_e_conj, const void* pre_b, int pre_b_conj,
                            const void* post_e, int post_e_conj, const void* post_b, int post_b_conj, int out_off,
                            int n_out, void* out, long long out_ld, void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (ny < 1 || nx < 1 || n < 1 || (axis != 0 && axis != 1)) return fail(h, PB_ERR_INVALID, "bad shape / axis");
     if (dir != -1 && dir != 1) return fail(h, PB_ERR_INVALID, "dir must be -1 or +1");
@@ -292,8 +288,7 @@ extern "C" int pb_axis_dft(pb_handle_t hh, int dtype, const void* in, int ny, in
 extern "C" int pb_czt_axis(pb_handle_t hh, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int K,
                            const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj, int out_off,
                            int n_out, double scale, void* out, long long out_ld, void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (ny < 1 || nx < 1 || K < 1 || (axis != 0 && axis != 1) || !H) return fail(h, PB_ERR_INVALID, "bad czt arguments");
     if (out_off < 0 || n_out < 1 || out_off + n_out > K) return fail(h, PB_ERR_INVALID, "output window outside the transform");
@@ -329,15 +324,12 @@ extern "C" int pb_czt_axis(pb_handle_t hh, int dtype, const void* in, int ny, in
 extern "C" int pb_angular_spectrum(pb_handle_t hh, int dtype, const void* in, int ny, int nx, int ky, int kx,
                                    const void* ty, const void* tx, const void* tf, int conj_tf, void* out, int oy,
                                    int ox, void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (ny < 1 || nx < 1 || ky < ny || kx < nx || oy < 1 || ox < 1 || oy > ky || ox > kx)
         return fail(h, PB_ERR_INVALID, "bad shapes");
     if (!tf && (!ty || !tx)) return fail(h, PB_ERR_INVALID, "need tf or both ty and tx");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int rc = try_tuned_angular_spectrum(h, dtype, in, ny, nx, ky, kx, ty, tx, tf, conj_tf, out, oy, ox, st);
-    if (rc != PB_ERR_UNSUPPORTED) return rc;
 
     const size_t cs = csize(dtype);
     void *t0 = nullptr, *t1 = nullptr;

@@ -164,6 +164,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -176,6 +189,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+
+// ---- tensor TMA (cp.async.bulk.tensor): strided gathers of 32-byte runs into contiguous shared memory ----
+__device__ __forceinline__ uint64_t l2_policy(int kind) {   // 0 evict_normal, 1 evict_first, 2 evict_last
+    uint64_t pol;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_hint(float4* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(float2* p, float2 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
 }
 
 template <int L> struct Geo {
@@ -272,6 +311,9 @@ struct FocusParams {
     // batch of independent fields in one launch pair (blockIdx.y in the column kernel; rows of all fields in the row
     // kernel's persistent loop): element strides of in / amp / out in units of their own scalar type
     long long in_bs, amp_bs, out_bs;
+    // v2 pipeline
+    int ntiles;             // column kernel: batch * N / T tiles, walked by a persistent grid
+    int hints;              // 1: L2 eviction hints (intermediate evict_last when written / evict_first when read, streams evict_first)
 };
 
 // ---- column pass: both half-transforms down T adjacent columns -------------------------------------
@@ -419,6 +461,440 @@ __global__ void __launch_bounds__(L / 16) focus_row_kernel(const FocusParams p) 
     }
 }
 
+// =====================================================================================================
+// v2 pipeline: same arithmetic, different traffic.
+//   * The intermediate is TILE-MAJOR: [field][plane p][j / 4][column tile = col / 4][j % 4][col % 4] complex64, i.e. the
+//     4 x 4 block (4 output rows of one plane, 4 adjacent columns) is one 128-byte line.  A warp of the column kernel
+//     (8 consecutive j x 4 columns) stores two full lines per instruction instead of eight 32-byte sectors in eight
+//     lines -- the LSU pressure (`lg_throttle`) of the row-major layout is gone.
+//   * The column kernel is persistent (one 512-thread CTA per SM walks the tiles of all fields of the launch) and takes
+//     its 4-column input tile by tensor TMA (box = 4 columns x 256 rows, 32-byte runs gathered into a contiguous
+//     [row][4] image that aliases the exchange buffers); the tile after next is requested as soon as the exchange
+//     buffers are free, so it lands while the last butterflies and the stores of the current tile run.
+//   * The row kernel gathers one intermediate row (512 runs of 32 bytes, 128 bytes apart) with two tensor-TMA boxes into
+//     the same contiguous row buffer the v1 kernel fills by a bulk copy; everything after that is the v1 code.
+// =====================================================================================================
+template <int L> struct Geo2 {
+    static constexpr int T = 4;                      // columns per tile
+    static constexpr int TILES = L / T;              // tiles per field
+    static constexpr int BOXR = 256;                 // rows per input box
+    static constexpr int NBOX_IN = L / BOXR;
+    static constexpr int BOXT = (TILES < 256 ? TILES : 256);   // tiles per row-gather box
+    static constexpr int NBOX_ROW = TILES / BOXT;
+};
+
+// Column kernel of the v2 pipeline.  One CTA per SM, 16 compute warps + 1 producer warp:
+//   * two independent 256-thread GROUPS (named barriers, own exchange buffers): group h computes half-transform h
+//     (h = 0: FFT_N(x) -> plane 0; h = 1: FFT_N(x w_K^n) (-dir i) -> plane 1) of the CTA's 4-column tiles.  A thread's
+//     two packed lanes are two ADJACENT COLUMNS, so both lanes use the same twiddle, the tile image is read with
+//     128-bit shared-memory loads and the tile-major stores are float4 (two columns): four full 128-byte lines per
+//     warp instruction.  The groups drift apart by up to one tile, so the exchange phases of one overlap the butterfly
+//     phases of the other (the v1 column kernel ran one 16-warp line group in lock step: FP32 pipe 25 %).
+//   * the 4-column x L-row input tile (64 KB) is gathered ONCE for both halves by tensor TMA (box = 4 columns x 256
+//     rows) into a staging area of its own; thread 0 requests tile i+1 at the first of its barriers after all 16 warps
+//     have the inputs of tile i in registers (a non-blocking mbarrier test at every barrier of group 0) -- most of a
+//     tile time of lead (the gather of 2048 32-byte runs takes ~2-3 us).
+//   * one twiddle plan for both halves (float2 entries, 17 KB): half 1's stage-1 twiddles are the plan's times the
+//     per-thread constant w_2L^t (its input ramp x w_K^n = x w_32^(n/NT) w_2L^t; the w_32 part is a compile-time constant).
+template <int L> struct Geo4 {
+    using G = Geo<L>;
+    static constexpr int XBUF = G::SBUF + 4;                 // +4 float4 = 16 words: adjacent buffers land on complementary banks
+    static constexpr int STAGE = 4 * XBUF;                   // float4 offset of the staging area (multiple of 8: 128-byte aligned)
+    static constexpr int PLAN2 = STAGE + 2 * L;              // float4 offset of the float2 plan
+    static constexpr int TW1 = 0, TW2 = 16 * G::NT, PLANLEN = 16 * G::NT + 15 * (G::NT / 16);   // float2 elements
+    static constexpr size_t BAR_OFF = (size_t)PLAN2 * 16 + (size_t)((PLANLEN * 8 + 15) / 16) * 16;
+    static constexpr size_t SMEM = BAR_OFF + 4 * sizeof(uint64_t);
+    static constexpr int THREADS = 4 * G::NT;                // 2 groups x 2 column pairs x NT
+};
+
+struct SyncGroup {   // named barrier of one 256-thread group (ids 1 and 2; 0 is __syncthreads)
+    int id, n;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+};
+
+// the first two radix-16 stages with ONE twiddle for both lanes: float2 plan in shared memory, times u (HALF 1)
+template <int L, bool INV, int HALF, class Sync>
+__device__ __forceinline__ void fft_two_stages_u(P2 (&v)[16], const int t, float4* __restrict__ S, const float2* __restrict__ tw1,
+                                                 const float2* __restrict__ tw2, const float2 u, Sync sync) {
+    using G = Geo<L>;
+    constexpr int NT = G::NT;
+    dft16<INV>(v);
+    if (HALF) v[0] = mul_tw<INV>(v[0], make_float4(u.x, u.x, u.y, u.y));
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+        float2 w = tw1[k * NT + t];
+        if (HALF) w = make_float2(fmaf(w.x, u.x, -w.y * u.y), fmaf(w.x, u.y, w.y * u.x));
+        v[k] = mul_tw<INV>(v[k], make_float4(w.x, w.x, w.y, w.y));
+    }
+    {
+        float4* __restrict__ d = S + t * 17;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = pack(v[k]);
+    }
+    sync();
+    {
+        const float4* __restrict__ s = S + pad16(t);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) v[n] = unpack(s[n * (NT + NT / 16)]);
+    }
+    sync();
+    dft16<INV>(v);
+    const int m = t >> 4, a = t & 15;
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+        const float2 w = tw2[(k - 1) * (NT / 16) + m];
+        v[k] = mul_tw<INV>(v[k], make_float4(w.x, w.x, w.y, w.y));
+    }
+    {
+        float4* __restrict__ d = S + m * 272 + a;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[17 * k] = pack(v[k]);
+    }
+    sync();
+}
+
+template <int L, bool INV, int HALF>
+__device__ __forceinline__ void focus_col4_group(const CUtensorMap& in_map, const FocusParams& p, float4* smem4, uint64_t* bar) {
+    using G = Geo<L>;
+    using G2 = Geo2<L>;
+    using G4 = Geo4<L>;
+    constexpr int NT = G::NT;
+    const int lt = threadIdx.x & (2 * NT - 1);                       // thread within the group
+    const int cp = lt & 1, t = lt >> 1;
+    const float4* __restrict__ stage = smem4 + G4::STAGE;
+    const float2* __restrict__ plan = reinterpret_cast<const float2*>(smem4 + G4::PLAN2);
+    float4* S = smem4 + (HALF * 2 + cp) * G4::XBUF;
+    const SyncGroup gsync{1 + HALF, 2 * NT};
+    const uint64_t pol_tmp = l2_policy(p.hints ? 2 : 0), pol_in = l2_policy(p.hints ? 1 : 0);
+    const bool issuer = HALF == 0 && lt == 0;
+    auto request_tile = [&](int ww) {   // one thread: gather tile ww = (field, column tile) into the staging area
+        const int fb = ww / G2::TILES, tile = ww - fb * G2::TILES;
+        mbar_expect_tx(bar + 1, (uint32_t)(L * 4 * sizeof(float2)));
+#pragma unroll
+        for (int b = 0; b < G2::NBOX_IN; ++b)
+            tma_load_3d(smem4 + G4::STAGE + b * G2::BOXR * 2, &in_map, tile * 4, b * G2::BOXR, fb, bar + 1, pol_in);
+    };
+    if (issuer) {
+        mbar_expect_tx(bar, (uint32_t)(G4::PLANLEN * sizeof(float2)));
+        bulk_g2s(smem4 + G4::PLAN2, p.plan, (uint32_t)(G4::PLANLEN * sizeof(float2)), bar);
+        if ((int)blockIdx.x < p.ntiles) request_tile(blockIdx.x);
+    }
+    const float sgn = (t & 1) ? -1.0f : 1.0f;
+    float2 u = make_float2(1.f, 0.f);
+    if (HALF) { float sn, cs; sincospif(-(float)t / (float)L, &sn, &cs); u = make_float2(cs, sn); }   // w_2L^t = exp(-i pi t / L)
+    mbar_wait(bar, 0);   // plan
+    int it = 0;
+    for (int w = blockIdx.x; w < p.ntiles; w += gridDim.x, ++it) {
+        const int fb = w / G2::TILES, tile = w - fb * G2::TILES;
+        bool pending = issuer && w + (int)gridDim.x < p.ntiles;   // the next tile exists and has not been requested
+        auto poll = [&](bool block) {   // request the next tile once every warp has released the staging area
+            if (!pending) return;
+            if (block) mbar_wait(bar + 2, it & 1);
+            else if (!mbar_test(bar + 2, it & 1)) return;
+            fence_proxy_async();
+            request_tile(w + gridDim.x);
+            pending = false;
+        };
+        auto sync = [&]() { gsync(); poll(false); };
+        P2 v[16];
+        {
+            float4 x[16];   // (col, col + 1) x (re, im)
+            mbar_wait(bar + 1, it & 1);
+            const float4* __restrict__ sg = stage + lt;   // ((n*NT + t)*2 + cp)
+#pragma unroll
+            for (int n = 0; n < 16; ++n) x[n] = sg[n * NT * 2];
+            // lanes = the two columns; HALF 1 multiplies both by w_32^n (the n-dependent part of the input ramp)
+#define PB_LANES2(n)                                                                                              \
+            if (HALF == 0) v[n] = {make_float2(x[n].x, x[n].z), make_float2(x[n].y, x[n].w)};                          \
+            else {                                                                                                     \
+                const P2 a_ = make_lanes<INV, n>(make_float2(x[n].x, x[n].y)), b_ = make_lanes<INV, n>(make_float2(x[n].z, x[n].w)); \
+                v[n] = {make_float2(a_.re.y, b_.re.y), make_float2(a_.im.y, b_.im.y)};                                 \
+            }
+            PB_LANES2(0) PB_LANES2(1) PB_LANES2(2) PB_LANES2(3) PB_LANES2(4) PB_LANES2(5) PB_LANES2(6) PB_LANES2(7)
+            PB_LANES2(8) PB_LANES2(9) PB_LANES2(10) PB_LANES2(11) PB_LANES2(12) PB_LANES2(13) PB_LANES2(14) PB_LANES2(15)
+#undef PB_LANES2
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(bar + 2);   // this warp holds its inputs: one of 16 releases of the staging area
+        }
+        fft_two_stages_u<L, INV, HALF>(v, t, S, plan + G4::TW1, plan + G4::TW2, u, sync);
+        fft_last_stage_load<L, INV>(v, t, S);
+        sync();   // this group's exchange buffers are free for its next tile
+#pragma unroll
+        for (int g = 0; g < G::GI; ++g) dftR<G::R3, INV>(v + g * G::R3);
+        // tile-major store: element (plane, j, tile, c) at ((plane*L/4 + j/4) * TILES + tile) * 16 + (j%4)*4 + c ; c = 2 cp
+        float4* __restrict__ dst = reinterpret_cast<float4*>(
+            p.tmp + fb * (2LL * L * L) + (long long)HALF * L * L + ((long long)(t >> 2) * G2::TILES + tile) * 16 + (t & 3) * 4 + 2 * cp);
+#pragma unroll
+        for (int g = 0; g < G::GI; ++g)
+#pragma unroll
+            for (int kk = 0; kk < G::R3; ++kk) {
+                const P2 y = v[g * G::R3 + kk];
+                const long long o = (long long)((g * NT + 256 * kk) >> 2) * (G2::TILES * 8);   // float4 units
+                // (-dir*i)^k with k = 2j + HALF; j has the parity of t.  HALF 1: times (-dir*i): forward (-im, re), inverse (im, -re)
+                float4 q;
+                if (HALF == 0) q = make_float4(sgn * y.re.x, sgn * y.im.x, sgn * y.re.y, sgn * y.im.y);
+                else q = INV ? make_float4(sgn * y.im.x, -sgn * y.re.x, sgn * y.im.y, -sgn * y.re.y)
+                             : make_float4(-sgn * y.im.x, sgn * y.re.x, -sgn * y.im.y, sgn * y.re.y);
+                st_hint(dst + o, q, pol_tmp);
+            }
+        poll(true);
+    }
+}
+
+template <int L, bool INV>
+__global__ void __launch_bounds__(Geo4<L>::THREADS) focus_col4_kernel(const __grid_constant__ CUtensorMap in_map, const FocusParams p) {
+    using G = Geo<L>;
+    using G2 = Geo2<L>;
+    using G4 = Geo4<L>;
+    extern __shared__ __align__(128) float4 smem4[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(smem4) + G4::BAR_OFF);   // [0] plan [1] tile full [2] tile free
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_init(bar + 2, 4 * G::NT / 32);   // one arrival per compute warp
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int grp = threadIdx.x / (2 * G::NT);
+    if (grp == 0) focus_col4_group<L, INV, 0>(in_map, p, smem4, bar);
+    else focus_col4_group<L, INV, 1>(in_map, p, smem4, bar);
+}
+
+template <int L, bool INV>
+__global__ void __launch_bounds__(L / 16) focus_row2_kernel(const __grid_constant__ CUtensorMap tmp_map, const FocusParams p) {
+    using G = Geo<L>;
+    using G2 = Geo2<L>;
+    constexpr int NT = G::NT, R3 = G::R3, GI = G::GI;
+    constexpr uint32_t ROW_BYTES = L * sizeof(float2);
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float4* S = reinterpret_cast<float4*>(smraw);                // SBUF exchange
+    float2* inb = reinterpret_cast<float2*>(S + G::SBUF);        // L-element input row
+    uint64_t* bar = reinterpret_cast<uint64_t*>(inb + L);        // 1 mbarrier
+    const int t = threadIdx.x;
+    int r = blockIdx.x;
+    const uint64_t pol_tmp = l2_policy(p.hints ? 1 : 0), pol_out = l2_policy(p.hints ? 1 : 0);
+    auto request_row = [&](int R) {   // one thread: gather intermediate row R = (field, plane, j) into `inb`
+        const int fb = R / (2 * L), rf = R - fb * (2 * L);
+        const int ph = rf / L, j = rf - ph * L;
+        const int grp = (fb * 2 + ph) * (L / 4) + (j >> 2);
+        mbar_expect_tx(bar, ROW_BYTES);
+#pragma unroll
+        for (int b = 0; b < G2::NBOX_ROW; ++b) tma_load_4d(inb + b * G2::BOXT * 4, &tmp_map, 0, j & 3, b * G2::BOXT, grp, bar, pol_tmp);
+    };
+    if (t == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        if (r < p.nrows) request_row(r);
+    }
+    __syncthreads();
+    const float sgn = ((t & 1) ? -1.0f : 1.0f) * p.scale;
+    for (int it = 0; r < p.nrows; ++it, r += gridDim.x) {
+        P2 v[16];
+        mbar_wait(bar, it & 1);
+        {
+            const float2* __restrict__ row = inb + t;
+#define PB_X(n) row[(n) * NT]
+            PB_MAKE_LANES_16(v, INV, PB_X)
+#undef PB_X
+        }
+        const int rn = r + gridDim.x;
+        auto sync_and_prefetch = [&]() {
+            __syncthreads();  // every thread holds its inputs in registers: the row buffer is free
+            if (t == 0 && rn < p.nrows) {
+                fence_proxy_async();
+                request_row(rn);
+            }
+        };
+        fft_two_stages<L, INV, 0>(v, t, S, p.plan + G::TW1, p.plan + G::TW2, sync_and_prefetch, SyncCta());
+        fft_last_stage_load<L, INV>(v, t, S);
+        __syncthreads();  // exchange buffer is free for the next row
+#pragma unroll
+        for (int g = 0; g < GI; ++g) dftR<R3, INV>(v + g * R3);
+        const int fb = r / (2 * L), rf = r - fb * (2 * L);   // field of the batch, row within its [2][L] planes
+        const int phs = rf / L, rr = rf - phs * L;
+        const int orow = (2 * rr + phs + L) & (2 * L - 1);  // fftshift along y
+        if (p.out_kind == PB_OUT_COMPLEX) {
+            float4* __restrict__ dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(p.out) + fb * p.out_bs + (long long)orow * p.out_ld);
+#pragma unroll
+            for (int g = 0; g < GI; ++g)
+#pragma unroll
+                for (int kk = 0; kk < R3; ++kk) {
+                    const int j = t + g * NT + 256 * kk;
+                    const P2 y = v[g * R3 + kk];
+                    const float4 o = INV ? make_float4(sgn * y.re.x, sgn * y.im.x, sgn * y.im.y, -sgn * y.re.y)
+                                         : make_float4(sgn * y.re.x, sgn * y.im.x, -sgn * y.im.y, sgn * y.re.y);
+                    st_hint(dst + ((j + L / 2) & (L - 1)), o, pol_out);
+                }
+        } else {
+            float2* __restrict__ dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + fb * p.out_bs + (long long)orow * p.out_ld);
+            const float2 s2 = make_float2(p.scale * p.scale, p.scale * p.scale);
+            const float2 wgt = make_float2(p.weight, p.weight);
+#pragma unroll
+            for (int g = 0; g < GI; ++g)
+#pragma unroll
+                for (int kk = 0; kk < R3; ++kk) {
+                    const int j = t + g * NT + 256 * kk;
+                    const P2 y = v[g * R3 + kk];
+                    float2 I = __fmul2_rn(s2, __ffma2_rn(y.re, y.re, __fmul2_rn(y.im, y.im)));
+                    float2* q = dst + ((j + L / 2) & (L - 1));
+                    if (p.out_kind == PB_OUT_ACCUMULATE) I = __ffma2_rn(wgt, I, *q);
+                    *q = I;
+                }
+        }
+    }
+}
+
+// Row kernel, second form: ONE 512-thread CTA per SM = four independent 128-thread line groups (named barriers, own
+// exchange buffer, own row buffer and mbarrier) that share the float2 twiddle plan of the column kernel in shared memory.
+// Against three 128-thread CTAs with the float4 plan in L1 (focus_row2_kernel): 16 instead of 12 warps per SM, stage-1
+// twiddles are 64-bit shared-memory loads (lane B's twiddle = lane A's times the per-thread constant w_2L^t, four scalar
+// FP32 operations) instead of 128-bit L1 loads whose latency shows up as the kernel's top stall, and the whole unified
+// array is shared memory (no L1 working set to protect).
+template <int L> struct GeoR4 {
+    using G = Geo<L>;
+    static constexpr size_t GROUP = (size_t)G::SBUF * 16 + (size_t)L * 8;       // exchange + row buffer, bytes (multiple of 128)
+    static constexpr size_t PLAN_OFF = 4 * GROUP;
+    static constexpr size_t BAR_OFF = PLAN_OFF + (size_t)((Geo4<L>::PLANLEN * 8 + 15) / 16) * 16;
+    static constexpr size_t SMEM = BAR_OFF + 8 * sizeof(uint64_t);
+};
+
+template <int L, bool INV>
+__global__ void __launch_bounds__(4 * L / 16) focus_row4_kernel(const __grid_constant__ CUtensorMap tmp_map, const FocusParams p) {
+    using G = Geo<L>;
+    using G2 = Geo2<L>;
+    using G4 = Geo4<L>;
+    using R4 = GeoR4<L>;
+    constexpr int NT = G::NT, R3 = G::R3, GI = G::GI;
+    constexpr uint32_t ROW_BYTES = L * sizeof(float2);
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int grp = threadIdx.x / NT, t = threadIdx.x - grp * NT;
+    float4* S = reinterpret_cast<float4*>(smraw + grp * R4::GROUP);      // this group's exchange buffer
+    float2* inb = reinterpret_cast<float2*>(S + G::SBUF);                 // ... and L-element input row
+    const float2* __restrict__ plan = reinterpret_cast<const float2*>(smraw + R4::PLAN_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + R4::BAR_OFF);   // [0] plan, [1 + grp] row of group grp
+    uint64_t* bar = bars + 1 + grp;
+    const uint64_t pol_tmp = l2_policy(p.hints ? 1 : 0), pol_out = l2_policy(p.hints ? 1 : 0);
+    auto request_row = [&](int R) {   // one thread: gather intermediate row R = (field, plane, j) into `inb`
+        const int fb = R / (2 * L), rf = R - fb * (2 * L);
+        const int ph = rf / L, j = rf - ph * L;
+        const int grow = (fb * 2 + ph) * (L / 4) + (j >> 2);
+        mbar_expect_tx(bar, ROW_BYTES);
+#pragma unroll
+        for (int b = 0; b < G2::NBOX_ROW; ++b) tma_load_4d(inb + b * G2::BOXT * 4, &tmp_map, 0, j & 3, b * G2::BOXT, grow, bar, pol_tmp);
+    };
+    int r = blockIdx.x * 4 + grp;
+    const int rstep = gridDim.x * 4;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bars, (uint32_t)(G4::PLANLEN * sizeof(float2)));
+        bulk_g2s(smraw + R4::PLAN_OFF, p.plan, (uint32_t)(G4::PLANLEN * sizeof(float2)), bars);
+    }
+    __syncthreads();
+    if (t == 0 && r < p.nrows) request_row(r);
+    const SyncGroup gsync{1 + grp, NT};
+    float2 u;
+    { float sn, cs; sincospif(-(float)t / (float)L, &sn, &cs); u = make_float2(cs, sn); }   // w_2L^t
+    const float sgn = ((t & 1) ? -1.0f : 1.0f) * p.scale;
+    mbar_wait(bars, 0);
+    for (int it = 0; r < p.nrows; ++it, r += rstep) {
+        P2 v[16];
+        mbar_wait(bar, it & 1);
+        {
+            const float2* __restrict__ row = inb + t;
+#define PB_X(n) row[(n) * NT]
+            PB_MAKE_LANES_16(v, INV, PB_X)
+#undef PB_X
+        }
+        const int rn = r + rstep;
+        // ---- stage 1
+        dft16<INV>(v);
+        v[0] = mul_tw<INV>(v[0], make_float4(1.0f, u.x, 0.0f, u.y));
+#pragma unroll
+        for (int k = 1; k < 16; ++k) {
+            const float2 w = plan[G4::TW1 + k * NT + t];
+            const float2 wb = make_float2(fmaf(w.x, u.x, -w.y * u.y), fmaf(w.x, u.y, w.y * u.x));
+            v[k] = mul_tw<INV>(v[k], make_float4(w.x, wb.x, w.y, wb.y));
+        }
+        {
+            float4* __restrict__ d = S + t * 17;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) d[k] = pack(v[k]);
+        }
+        gsync();   // every thread of the group holds its inputs in registers: the row buffer is free
+        if (t == 0 && rn < p.nrows) {
+            fence_proxy_async();
+            request_row(rn);
+        }
+        {
+            const float4* __restrict__ s4 = S + pad16(t);
+#pragma unroll
+            for (int n = 0; n < 16; ++n) v[n] = unpack(s4[n * (NT + NT / 16)]);
+        }
+        gsync();
+        // ---- stage 2
+        dft16<INV>(v);
+        {
+            const int m = t >> 4, a = t & 15;
+#pragma unroll
+            for (int k = 1; k < 16; ++k) {
+                const float2 w = plan[G4::TW2 + (k - 1) * (NT / 16) + m];
+                v[k] = mul_tw<INV>(v[k], make_float4(w.x, w.x, w.y, w.y));
+            }
+            float4* __restrict__ d = S + m * 272 + a;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) d[17 * k] = pack(v[k]);
+        }
+        gsync();
+        fft_last_stage_load<L, INV>(v, t, S);
+        gsync();  // exchange buffer is free for the next row
+#pragma unroll
+        for (int g = 0; g < GI; ++g) dftR<R3, INV>(v + g * R3);
+        const int fb = r / (2 * L), rf = r - fb * (2 * L);   // field of the batch, row within its [2][L] planes
+        const int phs = rf / L, rr = rf - phs * L;
+        const int orow = (2 * rr + phs + L) & (2 * L - 1);  // fftshift along y
+        if (p.out_kind == PB_OUT_COMPLEX) {
+            float4* __restrict__ dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(p.out) + fb * p.out_bs + (long long)orow * p.out_ld);
+#pragma unroll
+            for (int g = 0; g < GI; ++g)
+#pragma unroll
+                for (int kk = 0; kk < R3; ++kk) {
+                    const int j = t + g * NT + 256 * kk;
+                    const P2 y = v[g * R3 + kk];
+                    const float4 o = INV ? make_float4(sgn * y.re.x, sgn * y.im.x, sgn * y.im.y, -sgn * y.re.y)
+                                         : make_float4(sgn * y.re.x, sgn * y.im.x, -sgn * y.im.y, sgn * y.re.y);
+                    st_hint(dst + ((j + L / 2) & (L - 1)), o, pol_out);
+                }
+        } else {
+            float2* __restrict__ dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + fb * p.out_bs + (long long)orow * p.out_ld);
+            const float2 s2 = make_float2(p.scale * p.scale, p.scale * p.scale);
+            const float2 wgt = make_float2(p.weight, p.weight);
+#pragma unroll
+            for (int g = 0; g < GI; ++g)
+#pragma unroll
+                for (int kk = 0; kk < R3; ++kk) {
+                    const int j = t + g * NT + 256 * kk;
+                    const P2 y = v[g * R3 + kk];
+                    float2 I = __fmul2_rn(s2, __ffma2_rn(y.re, y.re, __fmul2_rn(y.im, y.im)));
+                    float2* q = dst + ((j + L / 2) & (L - 1));
+                    if (p.out_kind == PB_OUT_ACCUMULATE) I = __ffma2_rn(wgt, I, *q);
+                    *q = I;
+                }
+        }
+    }
+}
+
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+template <class K> int set_smem_attrs(Handle* h, K kernel, size_t smem, int ctas_per_sm) {
+    if (!attr_needed(h, reinterpret_cast<const void*>(kernel))) return PB_OK;
+    PB_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int pct = (int)std::min<size_t>(100, ((size_t)ctas_per_sm * (smem + 1024) * 100 + h->max_smem_optin - 1) / h->max_smem_optin);
+    if (const char* e = getenv("PB_CARVEOUT_PCT")) pct = atoi(e);
+    PB_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    return PB_OK;
+}
+
 // plan table, see Geo<L>
 template <int L>
 int get_focus_plan(Handle* h, const float4** out) {
@@ -450,33 +926,44 @@ int get_focus_plan(Handle* h, const float4** out) {
     return PB_OK;
 }
 
+// column-kernel plan of the v2 pipeline: float2 entries, one twiddle for both lanes (see Geo4)
+template <int L>
+int get_col4_plan(Handle* h, const float2** out) {
+    using G4 = Geo4<L>;
+    using G = Geo<L>;
+    TwKey key{L, PB_C64, 13};
+    auto it = h->tables.find(key);
+    if (it != h->tables.end()) { *out = reinterpret_cast<const float2*>(it->second); return PB_OK; }
+    std::vector<std::complex<double>> tab(G4::PLANLEN);
+    auto w = [&](long long num, long long den) {  // exp(-2 pi i num/den), argument reduced exactly
+        num %= den;
+        const double a = -2.0 * 3.14159265358979323846 * (double)num / (double)den;
+        return std::complex<double>(cos(a), sin(a));
+    };
+    for (int k = 0; k < 16; ++k)
+        for (int t = 0; t < G::NT; ++t) tab[G4::TW1 + k * G::NT + t] = w((long long)t * k, L);
+    for (int k = 1; k < 16; ++k)
+        for (int m = 0; m < G::NT / 16; ++m) tab[G4::TW2 + (k - 1) * (G::NT / 16) + m] = w(16LL * m * k, L);
+    const void* d = nullptr;
+    PB_TRY(upload_table(h, key, tab, &d));
+    *out = reinterpret_cast<const float2*>(d);
+    return PB_OK;
+}
+
 template <int L, bool INV>
 int launch_focus(Handle* h, FocusParams p, int batch, cudaStream_t st) {
     using G = Geo<L>;
     constexpr int T = 4;
     const size_t smem_col = (size_t)(T * (G::SBUF + 2) + G::PLAN) * sizeof(float4) + 2 * sizeof(uint64_t);
     const size_t smem_row = (size_t)G::SBUF * sizeof(float4) + (size_t)L * sizeof(float2) + 2 * sizeof(uint64_t);
-    static int row_ctas = 0;
-    if (!row_ctas) {
-        PB_CUDA(h, cudaFuncSetAttribute(focus_col_kernel<L, INV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
-        PB_CUDA(h, cudaFuncSetAttribute(focus_row_kernel<L, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
-        int n = 0;
-        PB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, focus_row_kernel<L, INV>, L / 16, smem_row));
-        n = n > 0 ? n : 1;
-        // Keep >= 64 KB of the unified L1/shared array as L1: the 34 KB twiddle plan is re-read by every
-        // line and must hit there.  (Left to itself the driver picks the 228 KB carve-out and the plan
-        // streams from L2 at ~300 cycles a load.)
-        const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
-        const int by_l1 = std::max(1, (int)((unified - l1_keep) / (smem_row + 1024)));
-        n = std::min(n, by_l1);
-        if (const char* e = getenv("PB_ROW_CTAS_PER_SM")) n = std::max(1, atoi(e));
-        row_ctas = n;
-        auto carve = [&](size_t bytes) { return (int)std::min<size_t>(100, (bytes * 100 + h->max_smem_optin - 1) / h->max_smem_optin); };
-        int row_pct = carve((size_t)n * (smem_row + 1024)), col_pct = carve(smem_col + 1024);
-        if (const char* e = getenv("PB_CARVEOUT_PCT")) row_pct = col_pct = atoi(e);
-        PB_CUDA(h, cudaFuncSetAttribute(focus_row_kernel<L, INV>, cudaFuncAttributePreferredSharedMemoryCarveout, row_pct));
-        PB_CUDA(h, cudaFuncSetAttribute(focus_col_kernel<L, INV, T>, cudaFuncAttributePreferredSharedMemoryCarveout, col_pct));
-    }
+    // Resident row CTAs per SM: as many as leave >= 64 KB of the unified L1/shared array as L1 -- the 34 KB twiddle plan is
+    // re-read by every line and must hit there.  (Left to itself the driver picks the 228 KB carve-out and the plan
+    // streams from L2 at ~300 cycles a load.)
+    const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
+    int row_ctas = std::max(1, (int)((unified - l1_keep) / (smem_row + 1024)));
+    if (const char* e = getenv("PB_ROW_CTAS_PER_SM")) row_ctas = std::max(1, atoi(e));
+    PB_TRY(set_smem_attrs(h, focus_col_kernel<L, INV, T>, smem_col, 1));
+    PB_TRY(set_smem_attrs(h, focus_row_kernel<L, INV>, smem_row, row_ctas));
     PB_TRY(get_focus_plan<L>(h, &p.plan));
     p.nrows = batch * 2 * L;
     focus_col_kernel<L, INV, T><<<dim3(L / T, batch), T * G::NT, smem_col, st>>>(p);
@@ -486,6 +973,87 @@ int launch_focus(Handle* h, FocusParams p, int batch, cudaStream_t st) {
     return PB_OK;
 }
 
+// ---- TMA descriptors, cached in the handle by (base pointer, geometry) -----------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_map_c64(Handle* h, const MapKey& key, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box, const CUtensorMap** out) {
+    auto it = h->maps.find(key);
+    if (it != h->maps.end()) { *out = &it->second; return PB_OK; }
+    static EncodeTiledFn fn = nullptr;   // a driver entry point: process-wide, not per device
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        void* f = nullptr;
+        PB_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+        if (!f || q != cudaDriverEntryPointSuccess) return fail(h, PB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    if (h->maps.size() > 256) h->maps.clear();
+    CUtensorMap m;
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, const_cast<void*>(key.base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, PB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    *out = &(h->maps[key] = m);
+    return PB_OK;
+}
+
+
+template <int L, bool INV>
+int launch_focus2(Handle* h, FocusParams p, int batch, cudaStream_t st) {
+    using G = Geo<L>;
+    using G2 = Geo2<L>;
+    using G4 = Geo4<L>;
+    const size_t smem_col = G4::SMEM;
+    const size_t smem_row = (size_t)G::SBUF * sizeof(float4) + (size_t)L * sizeof(float2) + 2 * sizeof(uint64_t);
+    auto colk = focus_col4_kernel<L, INV>;
+    // resident CTAs per SM: rows -- as many as leave >= 64 KB of the unified L1/shared array as L1 (the 34 KB twiddle plan
+    // is re-read by every line and must hit there; left alone the driver picks the 228 KB carve-out and the plan streams
+    // from L2 at ~300 cycles a load); columns -- two 256-thread CTAs (the register file holds no more)
+    static const int row_ctas_env = env_int("PB_ROW_CTAS_PER_SM", 0);
+    const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
+    const int row_ctas = row_ctas_env > 0 ? row_ctas_env : std::max(1, (int)((unified - l1_keep) / (smem_row + 1024)));
+    PB_TRY(set_smem_attrs(h, colk, smem_col, 1));
+    PB_TRY(set_smem_attrs(h, focus_row2_kernel<L, INV>, smem_row, row_ctas));
+    PB_TRY(get_focus_plan<L>(h, &p.plan));
+    const float4* plan_row = p.plan;
+    const float2* plan_col = nullptr;
+    PB_TRY(get_col4_plan<L>(h, &plan_col));
+    p.nrows = batch * 2 * L;
+    p.ntiles = batch * G2::TILES;
+    static const int hints = env_int("PB_FOCUS_L2_HINTS", 1);
+    p.hints = hints;
+    const CUtensorMap *in_map = nullptr, *tmp_map = nullptr;
+    {   // intermediate: [group = (field, plane, j/4)][tile][j%4][c]
+        const cuuint64_t dims[4] = {4, 4, (cuuint64_t)G2::TILES, (cuuint64_t)batch * 2 * (L / 4)};
+        const cuuint64_t str[3] = {32, 128, (cuuint64_t)G2::TILES * 128};
+        const cuuint32_t box[4] = {4, 1, (cuuint32_t)G2::BOXT, 1};
+        PB_TRY(get_map_c64(h, MapKey{p.tmp, 1, L, batch, 0, 0}, 4, dims, str, box, &tmp_map));
+    }
+    {   // input: (field, row, column) complex64; box = one 4-column run of 256 rows
+        const cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)L, (cuuint64_t)batch};
+        const cuuint64_t str[2] = {(cuuint64_t)p.in_ld * 8, (cuuint64_t)(batch > 1 ? p.in_bs : (long long)L * p.in_ld) * 8};
+        const cuuint32_t box[3] = {4, (cuuint32_t)G2::BOXR, 1};
+        PB_TRY(get_map_c64(h, MapKey{p.in, 2, L, batch, p.in_ld, batch > 1 ? p.in_bs : 0}, 3, dims, str, box, &in_map));
+    }
+    // column pass: one CTA per SM walks the tiles of all fields of the launch
+    p.plan = reinterpret_cast<const float4*>(plan_col);
+    colk<<<std::min(h->sm_count, p.ntiles), G4::THREADS, smem_col, st>>>(*in_map, p);
+    PB_LAUNCH_CHECK(h);
+    static const int row_version = env_int("PB_ROW_V", 4);
+    if (row_version == 4) {   // four line groups per CTA, plan in shared memory
+        PB_TRY(set_smem_attrs(h, focus_row4_kernel<L, INV>, GeoR4<L>::SMEM, 1));
+        focus_row4_kernel<L, INV><<<std::min(h->sm_count, (p.nrows + 3) / 4), 4 * G::NT, GeoR4<L>::SMEM, st>>>(*tmp_map, p);
+    } else {
+        p.plan = plan_row;
+        focus_row2_kernel<L, INV><<<std::min(h->sm_count * row_ctas, p.nrows), L / 16, smem_row, st>>>(*tmp_map, p);
+    }
+    PB_LAUNCH_CHECK(h);
+    return PB_OK;
+}
 
 // =====================================================================================================
 // Register-engine version of the generic axis pass (AxisPass semantics, complex64 in/out) for
@@ -641,15 +1209,13 @@ int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     using G = Geo<L>;
     constexpr int TP = COLS ? (L >= 4096 ? 2 : 2) : 1;
     const size_t smem = (size_t)TP * (G::SBUF + 2) * sizeof(float4);
-    static bool attr = false;
-    if (!attr) {
+    if (attr_needed(h, reinterpret_cast<const void*>(axis_reg_kernel<L, INV, COLS, TP, RT>))) {
         PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // keep >= 64 KB of L1 for the twiddle tables (see launch_focus)
         const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
         const int ctas = std::max<int>(1, (int)((unified - l1_keep) / (smem + 1024)));
         const int pct = (int)std::min<size_t>(100, ((size_t)ctas * (smem + 1024) * 100 + h->max_smem_optin - 1) / h->max_smem_optin);
         PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        attr = true;
     }
     const float2 *tw1 = nullptr, *tw2 = nullptr;
     PB_TRY(get_plain_plan<L>(h, &tw1, &tw2));
@@ -727,10 +1293,17 @@ int try_tuned_fft2_batch(Handle* h, int dtype, const void* in, int in_kind, cons
         p.plan = nullptr;
         p.out = reinterpret_cast<char*>(out) + (size_t)b0 * out_bs * out_elt;
         p.out_ld = out_ld; p.out_kind = out_kind; p.scale = (float)scale; p.weight = (float)weight;
-        p.nrows = 0;
+        p.nrows = 0; p.ntiles = 0; p.hints = 0;
         p.in_bs = in_bs; p.amp_bs = amp_bs; p.out_bs = out_bs;
         int rc;
-        if (dir < 0) rc = N == 512 ? launch_focus<512, false>(h, p, nb, st) : N == 1024 ? launch_focus<1024, false>(h, p, nb, st) : launch_focus<2048, false>(h, p, nb, st);
+        static const int version = env_int("PB_FOCUS_V", 2);
+        // v2 takes its input tiles by tensor TMA: complex input, 16-byte aligned base and even pitches; everything else
+        // (the fused phase-screen input, odd pitches) runs the v1 kernels
+        const bool v2_ok = in_kind == PB_IN_COMPLEX && !((uintptr_t)p.in & 15) && !(in_ld & 1) && !(in_bs & 1);
+        if (version >= 2 && v2_ok) {
+            if (dir < 0) rc = N == 512 ? launch_focus2<512, false>(h, p, nb, st) : N == 1024 ? launch_focus2<1024, false>(h, p, nb, st) : launch_focus2<2048, false>(h, p, nb, st);
+            else rc = N == 512 ? launch_focus2<512, true>(h, p, nb, st) : N == 1024 ? launch_focus2<1024, true>(h, p, nb, st) : launch_focus2<2048, true>(h, p, nb, st);
+        } else if (dir < 0) rc = N == 512 ? launch_focus<512, false>(h, p, nb, st) : N == 1024 ? launch_focus<1024, false>(h, p, nb, st) : launch_focus<2048, false>(h, p, nb, st);
         else rc = N == 512 ? launch_focus<512, true>(h, p, nb, st) : N == 1024 ? launch_focus<1024, true>(h, p, nb, st) : launch_focus<2048, true>(h, p, nb, st);
         if (rc != PB_OK) return rc;
     }
@@ -744,9 +1317,5 @@ int try_tuned_fft2(Handle* h, int dtype, const void* in, int in_kind, const void
                                 shift_in, shift_out, out, out_kind, weight, oy, ox, out_ld, 0, st);
 }
 
-int try_tuned_angular_spectrum(Handle*, int, const void*, int, int, int, int, const void*, const void*, const void*,
-                               int, void*, int, int, cudaStream_t) {
-    return PB_ERR_UNSUPPORTED;
-}
 
 }  // namespace pb

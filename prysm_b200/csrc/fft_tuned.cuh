@@ -18,8 +18,6 @@ int try_tuned_fft2_batch(Handle* h, int dtype, const void* in, int in_kind, cons
                          int dir, double scale, int shift_in, int shift_out, void* out, int out_kind, double weight,
                          int oy, int ox, long long out_ld, long long out_bs, cudaStream_t st);
 
-int try_tuned_angular_spectrum(Handle* h, int dtype, const void* in, int ny, int nx, int ky, int kx, const void* ty,
-                               const void* tx, const void* tf, int conj_tf, void* out, int oy, int ox,
-                               cudaStream_t st);
+
 
 }  // namespace pb

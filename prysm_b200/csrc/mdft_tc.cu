@@ -340,11 +340,8 @@ int launch_gemm(Handle* h, const float* Ahi, const float* Alo, const float* Bhi,
     PB_TRY(make_map(h, &mAlo, Alo, M, K, BM));
     PB_TRY(make_map(h, &mBhi, Bhi, N, K, BN));
     PB_TRY(make_map(h, &mBlo, Blo, N, K, BN));
-    static bool attr = false;
-    if (!attr) {
+    if (attr_needed(h, reinterpret_cast<const void*>(tc_gemm_kernel)))
         PB_CUDA(h, cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        attr = true;
-    }
     dim3 grid(M / BM, N / BN, splits);
     tc_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, gp);
     PB_LAUNCH_CHECK(h);
@@ -365,10 +362,6 @@ bool mdft_tc_shape_ok(int my, int ny, int mx, int nx) {
     return my % 128 == 0 && mx % 128 == 0 && ny % 128 == 0 && nx % 16 == 0 && ny >= 128 && nx >= 16;
 }
 
-int try_mdft_tc(Handle*, int, const void*, const void*, int, int, int, int, const void*, void*, double, int, int, void*,
-                cudaStream_t) {
-    return PB_ERR_UNSUPPORTED;  // the tensor-core path needs the expanded bases: see pb_mdft_tc_apply
-}
 
 }  // namespace pb
 
@@ -377,8 +370,7 @@ using namespace pb;
 extern "C" int pb_mdft_tc_supported(int my, int ny, int mx, int nx) { return mdft_tc_shape_ok(my, ny, mx, nx) ? 1 : 0; }
 
 extern "C" int pb_mdft_tc_expand(pb_handle_t hh, const void* E, int m, int n, void* hi, void* lo, void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (m < 1 || n < 1 || !E || !hi || !lo) return fail(h, PB_ERR_INVALID, "bad expand arguments");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long tot = (long long)m * n;
@@ -398,11 +390,12 @@ extern "C" long long pb_mdft_tc_work_bytes(int my, int ny, int mx, int nx) {
 extern "C" int pb_mdft_tc_apply(pb_handle_t hh, const void* ExB_hi, const void* ExB_lo, const void* EyB_hi,
                                 const void* EyB_lo, int my, int ny, int mx, int nx, const void* a, void* out, double norm,
                                 void* work, void* stream) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h) return PB_ERR_INVALID;
+    PB_ENTER(hh);
     if (!mdft_tc_shape_ok(my, ny, mx, nx)) return fail(h, PB_ERR_UNSUPPORTED, "shape not covered by the tensor-core MDFT");
     if (!ExB_hi || !ExB_lo || !EyB_hi || !EyB_lo || !a || !out || !work) return fail(h, PB_ERR_INVALID, "null pointer");
-    if (((uintptr_t)a & 15) || ((uintptr_t)work & 1023)) return fail(h, PB_ERR_INVALID, "data / work must be 16 B / 1 KB aligned");
+    // TMA needs 16-byte aligned global base addresses (the 1 KB alignment of the swizzle atoms is a shared-memory matter);
+    // every sub-buffer of `work` below starts at a multiple of 16 bytes given the shape constraints
+    if (((uintptr_t)a & 15) || ((uintptr_t)work & 15)) return fail(h, PB_ERR_INVALID, "data / work must be 16-byte aligned");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int splits = pick_splits(ny);
     // 2 K-blocks (8 main accumulation steps) per drain: < 1e-6 of the fp64 result at any K (measured:

@@ -229,8 +229,7 @@ static int build_terms(Handle* h, int k, const int* n_host, const int* m_host, c
 using namespace pb;
 
 #define PB_HANDLE(hh)                                   \
-    Handle* h = reinterpret_cast<Handle*>(hh);          \
-    if (!h) return PB_ERR_INVALID;                      \
+    PB_ENTER(hh);                      \
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128"); \
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
 

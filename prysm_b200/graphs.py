@@ -14,6 +14,8 @@ construction from host coordinates (`prepare_executor`, `prepare_multiresolution
 """
 import torch
 
+from . import _capi
+
 
 class CapturedGraph:
     """A replayable capture of fn(*inputs).  Tensor inputs are copied into static buffers owned by the capture;
@@ -25,6 +27,8 @@ class CapturedGraph:
         if dev is None or dev.type != 'cuda':
             raise ValueError('capture() needs at least one CUDA tensor input')
         self._stream = torch.cuda.Stream(device=dev)
+        self._key = (dev.index if dev.index is not None else torch.cuda.current_device(), self._stream.cuda_stream)
+        _capi.pin_handle(*self._key)     # the graph replays into this stream's handle (tables + scratch): keep it alive
         self._stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self._stream):          # warm-up on the capture stream: its handle builds its tables here
             for _ in range(max(1, warmup)):
@@ -46,6 +50,12 @@ class CapturedGraph:
                 raise ValueError('non-tensor arguments are baked into the capture and cannot change')
         self._graph.replay()
         return self._static_out
+
+    def close(self):
+        """Release the graph and the engine state of its capture stream."""
+        self._graph = None
+        self._static_out = None
+        _capi.release_handle(*self._key)
 
     @property
     def inputs(self):

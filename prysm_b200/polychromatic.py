@@ -33,11 +33,12 @@ def _world(group):
     return 0, 1
 
 
-def sharded_incoherent_sum(n_units, accumulate_unit, plane, group=None, dst=None):
+def sharded_incoherent_sum(n_units, accumulate_unit, plane, group=None, dst=None, shard=True):
     """Generic driver.  `accumulate_unit(i, plane)` must add unit i's weighted intensity into `plane`
     (a tensor on this rank's device).  After the local loop the planes are summed across ranks:
-    onto `dst` if given (other ranks' planes are left as their partial sums), else onto every rank."""
-    rank, world = _world(group)
+    onto `dst` if given (other ranks' planes are left as their partial sums), else onto every rank.
+    shard=False runs every unit on the calling rank with no exchange (the single-GPU form inside a multi-rank job)."""
+    rank, world = _world(group) if shard else (0, 1)
     for i in shard_units(n_units, rank, world):
         accumulate_unit(i, plane)
     if world > 1:
@@ -49,7 +50,7 @@ def sharded_incoherent_sum(n_units, accumulate_unit, plane, group=None, dst=None
 
 
 def polychromatic_psf(amplitude, phase, wavelengths, weights, dx, efl, focal_dx, focal_samples, kind='czt',
-                      shift=(0, 0), group=None, dst=None):
+                      shift=(0, 0), group=None, dst=None, shard=True):
     """Weighted incoherent PSF over `wavelengths` on a common focal grid.
 
     Per wavelength (exactly the reference recipe): from_amp_and_phase -> prepare_executor(kind) ->
@@ -66,15 +67,21 @@ def polychromatic_psf(amplitude, phase, wavelengths, weights, dx, efl, focal_dx,
         raise ValueError('one weight per wavelength is required')
     if isinstance(focal_samples, int):
         focal_samples = (focal_samples, focal_samples)
-    plane = torch.zeros(tuple(focal_samples), dtype=opd.dtype, device=opd.device)
+    # The executors compute in config.precision whatever the OPD's storage type is (`_prep` casts the field to
+    # config.complex_dtype), so the accumulation plane is allocated in THAT real type -- never in opd.dtype -- and
+    # `_ops.intensity` refuses a plane whose type does not match the field it is handed.
+    plane = torch.zeros(tuple(focal_samples), dtype=config.real_dtype, device=opd.device)
+    cplx_of_plane = torch.complex64 if plane.dtype == torch.float32 else torch.complex128
 
     def unit(i, acc):
         wf = P.Wavefront.from_amp_and_phase(amp, opd, float(wavelengths[i]), dx)
         ex = wf.prepare_executor(efl, focal_dx, focal_samples, shift=shift, kind=kind)
         field = wf.focus_dft(ex).data
+        if field.dtype != cplx_of_plane:
+            field = field.to(cplx_of_plane)
         _ops.intensity(field, weight=float(weights[i]), out=acc)
 
-    return sharded_incoherent_sum(len(wavelengths), unit, plane, group=group, dst=dst)
+    return sharded_incoherent_sum(len(wavelengths), unit, plane, group=group, dst=dst, shard=shard)
 
 
 def polychromatic_psf_fft(amplitude, phase, wavelengths, weights, Q=2, group=None, dst=None):
