@@ -85,7 +85,7 @@ int pb_fft2(pb_handle_t h, int dtype,
             void* stream);
 /* pb_fft2 over `batch` independent fields in one call: field b starts at in + b*in_bs, amp + b*amp_bs (0 = one
  * amplitude shared by all) and out + b*out_bs, strides in elements of the respective array's scalar type.  On the
- * fused focus shapes the fields share launches (two per launch pair by default), which evens out the 3.46-wave
+ * fused focus shapes the fields share launches (eight per launch pair by default), which evens out the 3.46-wave
  * column pass and the 9.2-round row pass of a single 2048^2 field; other shapes run field by field.  The reference
  * has no batch form: fft.py:7-25 is called once per wavefront. */
 int pb_fft2_batch(pb_handle_t h, int dtype, const void* in, int in_kind, const void* amp, int amp_kind,
@@ -136,6 +136,14 @@ int pb_czt_plan(pb_handle_t h, int dtype, int N, int M, int K, double shift, dou
 int pb_angular_spectrum(pb_handle_t h, int dtype, const void* in, int ny, int nx,
                         int ky, int kx, const void* ty, const void* tx, const void* tf,
                         int conj_tf, void* out, int oy, int ox, void* stream);
+
+/* The same with the field multiplied by a complex (ny,nx) `screen` (conj_screen: by its conjugate) inside the first
+ * transform pass: one step `wf = (wf * screen).free_space(dz)` of a plane-to-plane chain without the separate
+ * elementwise pass.  Replaces prysm/propagation/wavefront.py:360-383 (Wavefront.__mul__) followed by
+ * prysm/propagation/angular_spectrum.py:9-42. */
+int pb_angular_spectrum_screen(pb_handle_t h, int dtype, const void* in, const void* screen, int conj_screen,
+                               int ny, int nx, int ky, int kx, const void* ty, const void* tx, const void* tf,
+                               int conj_tf, void* out, int oy, int ox, void* stream);
 
 /* the two separable factors exp(-i*pi*wvl_mm*z*k^2), k = fftfreq(n, dx) rounded to the working
  * precision first (prysm/propagation/angular_spectrum.py:102-113).  ty: ky values, tx: kx. */

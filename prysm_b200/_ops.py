@@ -235,7 +235,9 @@ def czt_axis(a, K, axis, pre_e, H, post_e, out_off, n_out, scale=1.0, pre_conj=F
     return out
 
 
-def angular_spectrum(field, k, ty=None, tx=None, tf=None, conj_tf=False, crop=None):
+def angular_spectrum(field, k, ty=None, tx=None, tf=None, conj_tf=False, crop=None, screen=None, conj_screen=False):
+    """pb_angular_spectrum; with `screen` (complex, same shape as the field) pb_angular_spectrum_screen: the field is
+    multiplied by the screen inside the first transform pass."""
     field = ascomplex(field).contiguous()
     ny, nx = field.shape
     ky, kx = k
@@ -244,6 +246,13 @@ def angular_spectrum(field, k, ty=None, tx=None, tf=None, conj_tf=False, crop=No
     if tf is not None:
         tf = tf.to(field.dtype).contiguous()
     h, st = _ctx(field)
+    if screen is not None:
+        if tuple(screen.shape) != (ny, nx):
+            raise ValueError(f'shape mismatch {(ny, nx)} vs {tuple(screen.shape)}')
+        screen = ascomplex(screen).to(field.dtype).contiguous()
+        h.check(lib.pb_angular_spectrum_screen(h.ptr, _CODE[field.dtype], _p(field), _p(screen), int(conj_screen), ny, nx, ky,
+                                               kx, _p(ty), _p(tx), _p(tf), int(conj_tf), _p(out), oy, ox, st))
+        return out
     h.check(lib.pb_angular_spectrum(h.ptr, _CODE[field.dtype], _p(field), ny, nx, ky, kx, _p(ty), _p(tx), _p(tf),
                                     int(conj_tf), _p(out), oy, ox, st))
     return out

@@ -43,6 +43,10 @@ __global__ void __launch_bounds__(512) axis_pass_kernel(const AxisPass p, const 
             const int li = pp - p.in_off;
             if (li >= 0 && li < p.n_in) {
                 v = load_input<R>(p, (long long)b * p.ibs + (long long)li * p.ies);
+                if (p.pre_mat) {
+                    C m = reinterpret_cast<const C*>(p.pre_mat)[(long long)b * p.pmi_bs + (long long)li * p.pmi_es];
+                    v = p.pre_mat_conj ? cmulc(v, m) : cmul(v, m);
+                }
                 if (p.pre_e) {
                     C m = reinterpret_cast<const C*>(p.pre_e)[j - p.pre_off];
                     v = p.pre_e_conj ? cmulc(v, m) : cmul(v, m);

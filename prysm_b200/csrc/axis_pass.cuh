@@ -9,7 +9,7 @@ namespace pb {
 // Logical model, for every batch b in [0, nb):
 //   u[j], j in [0, L):   j >= Llog -> 0 ; else p = (j + rot_in) mod Llog,
 //                        v = (in_off <= p < in_off + n_in) ? load(b, p - in_off) : 0
-//                        u[j] = v * pre_e[j - pre_off] * pre_b[b]            (multipliers optional)
+//                        u[j] = v * pre_mat(b, p - in_off) * pre_e[j - pre_off] * pre_b[b]   (multipliers optional)
 //   U = DFT_L(u) with exp(dir * 2*pi*i*jk/L)
 //   out(b, q), q in [0, n_out):  k = (q + crop_off - rot_out) mod Llog
 //                        U[k] * post_e[k - post_off] * post_b[b] * post_mat(b, q) * scale
@@ -30,6 +30,8 @@ struct AxisPass {
     const void* pre_e = nullptr; int pre_off = 0; int pre_e_conj = 0;
     const void* pre_e2 = nullptr; int pre_off2 = 0; int pre_e2_conj = 0;
     const void* pre_b = nullptr; int pre_b_conj = 0;
+    // full-matrix pre-multiplier, indexed like the input (the between-plane phase screen of a free-space chain)
+    const void* pre_mat = nullptr; long long pmi_bs = 0, pmi_es = 0; int pre_mat_conj = 0;
     // transform
     int dir = -1;
     // output

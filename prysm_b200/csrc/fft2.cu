@@ -133,7 +133,7 @@ static int axis_dft(Handle* h, AxisPass p, cudaStream_t st) {
     b.in = tmp; b.in_kind = PB_IN_COMPLEX; b.amp = nullptr;
     b.ibs = a.obs; b.ies = a.oes;
     b.n_in = M; b.in_off = 0; b.rot_in = 0;
-    b.pre_e = nullptr; b.pre_e2 = nullptr; b.pre_b = nullptr;
+    b.pre_e = nullptr; b.pre_e2 = nullptr; b.pre_b = nullptr; b.pre_mat = nullptr;
     b.dir = +1;
     if (p.post_e2) return fail(h, PB_ERR_UNSUPPORTED, "two post-multipliers on a non power-of-two axis");
     b.post_e2 = p.post_e; b.post_off2 = p.post_off; b.post_e2_conj = p.post_e_conj;
@@ -321,22 +321,21 @@ extern "C" int pb_czt_axis(pb_handle_t hh, int dtype, const void* in, int ny, in
     return axis_dft(h, b, st);
 }
 
-extern "C" int pb_angular_spectrum(pb_handle_t hh, int dtype, const void* in, int ny, int nx, int ky, int kx,
-                                   const void* ty, const void* tx, const void* tf, int conj_tf, void* out, int oy,
-                                   int ox, void* stream) {
-    PB_ENTER(hh);
+static int angular_spectrum_impl(Handle* h, int dtype, const void* in, int ny, int nx, int ky, int kx, const void* ty,
+                                 const void* tx, const void* tf, int conj_tf, const void* screen, int conj_screen, void* out,
+                                 int oy, int ox, cudaStream_t st) {
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (ny < 1 || nx < 1 || ky < ny || kx < nx || oy < 1 || ox < 1 || oy > ky || ox > kx)
         return fail(h, PB_ERR_INVALID, "bad shapes");
     if (!tf && (!ty || !tx)) return fail(h, PB_ERR_INVALID, "need tf or both ty and tx");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
     const size_t cs = csize(dtype);
     void *t0 = nullptr, *t1 = nullptr;
     PB_TRY(ensure_scratch(h, 0, (size_t)ky * kx * cs, &t0));
     PB_TRY(ensure_scratch(h, 1, (size_t)ky * kx * cs, &t1));
-    AxisPass p;  // rows forward: ny populated rows -> t0 (ny, kx)
+    AxisPass p;  // rows forward (times the phase screen, if any): ny populated rows -> t0 (ny, kx)
     p.dtype = dtype; p.in = in; p.ibs = nx; p.ies = 1; p.nb = ny;
+    p.pre_mat = screen; p.pmi_bs = nx; p.pmi_es = 1; p.pre_mat_conj = conj_screen;
     p.Llog = kx; p.n_in = nx; p.in_off = ceil_half(kx - nx);
     p.dir = -1; p.out = t0; p.obs = kx; p.oes = 1; p.n_out = kx;
     PB_TRY(axis_dft(h, p, st));
@@ -376,4 +375,21 @@ extern "C" int pb_angular_spectrum(pb_handle_t hh, int dtype, const void* in, in
     s.out = out; s.obs = ox; s.oes = 1; s.n_out = ox; s.crop_off = ceil_half(kx - ox);
     s.scale = 1.0 / ((double)ky * (double)kx);
     return axis_dft(h, s, st);
+}
+
+extern "C" int pb_angular_spectrum(pb_handle_t hh, int dtype, const void* in, int ny, int nx, int ky, int kx,
+                                   const void* ty, const void* tx, const void* tf, int conj_tf, void* out, int oy,
+                                   int ox, void* stream) {
+    PB_ENTER(hh);
+    return angular_spectrum_impl(h, dtype, in, ny, nx, ky, kx, ty, tx, tf, conj_tf, nullptr, 0, out, oy, ox,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pb_angular_spectrum_screen(pb_handle_t hh, int dtype, const void* in, const void* screen, int conj_screen,
+                                          int ny, int nx, int ky, int kx, const void* ty, const void* tx, const void* tf,
+                                          int conj_tf, void* out, int oy, int ox, void* stream) {
+    PB_ENTER(hh);
+    if (!screen) return fail(h, PB_ERR_INVALID, "null screen");
+    return angular_spectrum_impl(h, dtype, in, ny, nx, ky, kx, ty, tx, tf, conj_tf, screen, conj_screen, out, oy, ox,
+                                 reinterpret_cast<cudaStream_t>(stream));
 }

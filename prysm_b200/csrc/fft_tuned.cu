@@ -737,8 +737,8 @@ __global__ void __launch_bounds__(L / 16) focus_row2_kernel(const __grid_constan
                     const P2 y = v[g * R3 + kk];
                     float2 I = __fmul2_rn(s2, __ffma2_rn(y.re, y.re, __fmul2_rn(y.im, y.im)));
                     float2* q = dst + ((j + L / 2) & (L - 1));
-                    if (p.out_kind == PB_OUT_ACCUMULATE) I = __ffma2_rn(wgt, I, *q);
-                    *q = I;
+                    if (p.out_kind == PB_OUT_ACCUMULATE) I = __ffma2_rn(wgt, I, ld_stream(q));
+                    st_hint(q, I, pol_out);
                 }
         }
     }
@@ -877,8 +877,8 @@ __global__ void __launch_bounds__(4 * L / 16) focus_row4_kernel(const __grid_con
                     const P2 y = v[g * R3 + kk];
                     float2 I = __fmul2_rn(s2, __ffma2_rn(y.re, y.re, __fmul2_rn(y.im, y.im)));
                     float2* q = dst + ((j + L / 2) & (L - 1));
-                    if (p.out_kind == PB_OUT_ACCUMULATE) I = __ffma2_rn(wgt, I, *q);
-                    *q = I;
+                    if (p.out_kind == PB_OUT_ACCUMULATE) I = __ffma2_rn(wgt, I, ld_stream(q));
+                    st_hint(q, I, pol_out);
                 }
         }
     }
@@ -1066,7 +1066,7 @@ __device__ __forceinline__ float2 cmul_s(float2 a, float2 b, int conj) {
                 : make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-template <int L, bool INV, bool COLS, int TP, bool RT>
+template <int L, bool INV, bool COLS, int TP, bool RT, bool PM>
 __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16) axis_reg_kernel(const AxisPass p, const float2* __restrict__ tw1,
                                                                             const float2* __restrict__ tw2) {
     using G = Geo<L>;
@@ -1102,6 +1102,27 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16) axis_reg_kernel(cons
             if (pre_b) { xa = cmul_s(xa, pbA, p.pre_b_conj); xb = cmul_s(xb, pbB, p.pre_b_conj); }
         }
         v[n] = {make_float2(xa.x, xb.x), make_float2(xa.y, xb.y)};
+    }
+    if (PM) {
+        // full-matrix pre-multiplier (the phase screen of a free-space chain), same access pattern as the input.  A loop of
+        // its own: the 32 loads are independent of the input loads above and of each other, so they overlap, and the
+        // product is one packed complex multiply per point (lane A x mA, lane B x mB).
+        const float2* __restrict__ pm = reinterpret_cast<const float2*>(p.pre_mat);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+            const int j = n * NT + t;
+            int pp = j + p.rot_in;
+            if (pp >= L) pp -= L;
+            const int li = pp - p.in_off;
+            if (li >= 0 && li < p.n_in) {
+                const long long om = (long long)b0 * p.pmi_bs + (long long)li * p.pmi_es;
+                float2 ma = make_float2(1.f, 0.f), mb = ma;
+                if (hasA) ma = ld_stream(pm + om);
+                if (hasB) mb = ld_stream(pm + om + p.pmi_bs);
+                const float4 w = make_float4(ma.x, mb.x, ma.y, mb.y);
+                v[n] = p.pre_mat_conj ? mul_tw<true>(v[n], w) : mul_tw<false>(v[n], w);
+            }
+        }
     }
     float4* S = smem4 + c * (G::SBUF + 2);
     fft_two_stages<L, INV, 2>(v, t, S, tw1, tw2, SyncCta(), SyncCta());
@@ -1204,24 +1225,24 @@ int get_plain_plan(Handle* h, const float2** tw1, const float2** tw2) {
     return PB_OK;
 }
 
-template <int L, bool INV, bool COLS, bool RT>
+template <int L, bool INV, bool COLS, bool RT, bool PM = false>
 int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     using G = Geo<L>;
     constexpr int TP = COLS ? (L >= 4096 ? 2 : 2) : 1;
     const size_t smem = (size_t)TP * (G::SBUF + 2) * sizeof(float4);
-    if (attr_needed(h, reinterpret_cast<const void*>(axis_reg_kernel<L, INV, COLS, TP, RT>))) {
-        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (attr_needed(h, reinterpret_cast<const void*>(axis_reg_kernel<L, INV, COLS, TP, RT, PM>))) {
+        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // keep >= 64 KB of L1 for the twiddle tables (see launch_focus)
         const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
         const int ctas = std::max<int>(1, (int)((unified - l1_keep) / (smem + 1024)));
         const int pct = (int)std::min<size_t>(100, ((size_t)ctas * (smem + 1024) * 100 + h->max_smem_optin - 1) / h->max_smem_optin);
-        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT, PM>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     const float2 *tw1 = nullptr, *tw2 = nullptr;
     PB_TRY(get_plain_plan<L>(h, &tw1, &tw2));
     const int lines_per_cta = 2 * TP;
     const int grid = (p.nb + lines_per_cta - 1) / lines_per_cta;
-    axis_reg_kernel<L, INV, COLS, TP, RT><<<grid, TP * G::NT, smem, st>>>(p, tw1, tw2);
+    axis_reg_kernel<L, INV, COLS, TP, RT, PM><<<grid, TP * G::NT, smem, st>>>(p, tw1, tw2);
     PB_LAUNCH_CHECK(h);
     return PB_OK;
 }
@@ -1229,6 +1250,10 @@ int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
 template <int L>
 int dispatch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     const bool cols = p.batch_contiguous != 0;
+    if (p.pre_mat) {   // the screened first pass of a free-space step: rows, plain transform
+        if (cols || p.roundtrip) return PB_ERR_UNSUPPORTED;
+        return p.dir < 0 ? launch_axis_reg<L, false, false, false, true>(h, p, st) : launch_axis_reg<L, true, false, false, true>(h, p, st);
+    }
     if (p.roundtrip) {
         if (p.dir < 0) return cols ? launch_axis_reg<L, false, true, true>(h, p, st) : launch_axis_reg<L, false, false, true>(h, p, st);
         return cols ? launch_axis_reg<L, true, true, true>(h, p, st) : launch_axis_reg<L, true, false, true>(h, p, st);

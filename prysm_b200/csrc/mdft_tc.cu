@@ -40,7 +40,7 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 32;           // BK fp32 = 128 B = one swizzle row
 constexpr int STAGES = 2;
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 384;   // warp 0 TMA, 1 MMA, 2-3 TMEM alloc + TF32 lo-split converters, 4-11 epilogue
 constexpr uint32_t A_TILE = BM * BK * 4;             // 16 KB
 constexpr uint32_t B_TILE = BN * BK * 4;             // 32 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // 96 KB
@@ -123,7 +123,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 struct GemmParams {
     int kblocks;        // K blocks of 32 handled by one CTA
     int chunk;          // K blocks accumulated in TMEM between drains of the main accumulator
-    int mode;           // 0: write complex transposed hi/lo (stage 1); 1: write fp32 transposed split-K partials
+    int mode;           // 0: write complex transposed (stage 1); 1: write fp32 transposed split-K partials
+    int conv_b;         // 1: the lo part of the B tiles is formed in shared memory too (nothing but fp32 A and B is loaded)
     float* out_hi;      // mode 0: T1^T hi as complex (float2) [N/2][ldo]; mode 1: ws [split][N][ldo]
     float* out_lo;      // mode 0: T1^T lo
     long long ldo;      // leading dimension of the transposed output, in output elements
@@ -133,16 +134,17 @@ struct GemmParams {
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmBhi,
+               const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* full = bars;              // [STAGES]  TMA -> MMA
     uint64_t* empty = bars + STAGES;    // [STAGES]  MMA -> TMA
-    uint64_t* tmem_full = bars + 2 * STAGES;       // MMA -> epilogue: a chunk is complete in TMEM
-    uint64_t* tmem_empty = bars + 2 * STAGES + 1;  // epilogue -> MMA: the main accumulator was drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+    uint64_t* conv = bars + 2 * STAGES; // [STAGES]  converters -> MMA: the lo tiles of the stage are in shared memory
+    uint64_t* tmem_full = bars + 3 * STAGES;       // MMA -> epilogue: a chunk is complete in TMEM
+    uint64_t* tmem_empty = bars + 3 * STAGES + 1;  // epilogue -> MMA: the main accumulator was drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -152,12 +154,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAhi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAlo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 64); }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 8);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -178,12 +179,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 unsigned char* st = smem + s * STAGE_BYTES;
-                mbar_expect_tx(&full[s], STAGE_BYTES);
+                mbar_expect_tx(&full[s], A_TILE + (p.conv_b ? B_TILE : 2 * B_TILE));
                 const int kc = (kb0 + kb) * BK;
-                tma_load_2d(st, &tmAhi, kc, m0, &full[s]);
-                tma_load_2d(st + A_TILE, &tmAlo, kc, m0, &full[s]);
+                tma_load_2d(st, &tmAhi, kc, m0, &full[s]);                 // fp32 A: read as TF32 it IS the hi part
                 tma_load_2d(st + 2 * A_TILE, &tmBhi, kc, n0, &full[s]);
-                tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBlo, kc, n0, &full[s]);
+                if (!p.conv_b) tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBlo, kc, n0, &full[s]);
             }
         }
     } else if (warp == 1) {
@@ -199,7 +199,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                     mbar_wait(tmem_empty, (c - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                mbar_wait(&full[s], ph);
+                mbar_wait(&conv[s], ph);   // TMA landed AND the converter warps wrote the lo tiles
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE);
@@ -214,6 +214,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 umma_commit(&empty[s]);   // frees the smem stage once these MMAs have read it
                 if (kin == CHUNK - 1 || kb == p.kblocks - 1) umma_commit(tmem_full);  // chunk complete
             }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===== converters: lo = x - tf32(x) for the A tile (and the B tile), element for element in the swizzled layout.
+        // The TF32 split used to be a streaming pre-pass over the whole input plus a second operand array; forming it on
+        // the tile in shared memory removes that pass and a third (or half) of the L2 -> SM operand traffic.
+        const int ct = threadIdx.x - 2 * 32;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            float4* st = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+            auto split = [&](const float4* hi, float4* lo, int n4) {
+#pragma unroll 4
+                for (int i = ct; i < n4; i += 64) {
+                    const float4 v = hi[i];
+                    lo[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                }
+            };
+            split(st, st + A_TILE / 16, A_TILE / 16);
+            if (p.conv_b) split(st + 2 * A_TILE / 16, st + (2 * A_TILE + B_TILE) / 16, B_TILE / 16);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+            mbar_arrive(&conv[s]);
         }
     } else if (warp >= 4) {
         // ===== epilogue: drain chunks into registers, then transposed global stores =====
@@ -253,13 +275,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         const int nb = n0 + half * 128;
         if (p.mode == 0) {
             float2* __restrict__ hi = reinterpret_cast<float2*>(p.out_hi);
-            float2* __restrict__ lo = reinterpret_cast<float2*>(p.out_lo);
 #pragma unroll
             for (int c = 0; c < 128; c += 2) {
-                const float re = tot[c], im = tot[c + 1];
                 const long long o = (long long)((nb + c) >> 1) * p.ldo + m;
-                hi[o] = make_float2(re, im);
-                lo[o] = make_float2(tf32_lo(re), tf32_lo(im));
+                hi[o] = make_float2(tot[c], tot[c + 1]);
             }
         } else {
             float* __restrict__ ws = p.out_hi + (long long)blockIdx.z * p.split_stride;
@@ -270,14 +289,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-}
-
-// lo part of an fp32 array under the TF32 split
-__global__ void split_lo_kernel(const float4* __restrict__ a, float4* __restrict__ lo, long long n4) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = a[i];
-        lo[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-    }
 }
 
 // complex basis E (m,n) -> real expansion (2m, 2n), hi and lo
@@ -333,17 +344,16 @@ int make_map(Handle* h, CUtensorMap* map, const void* base, long long rows, long
 }
 
 // C'(M x N) = A'(M x K) @ B'(N x K)^T on the tensor cores; see GemmParams for the output modes
-int launch_gemm(Handle* h, const float* Ahi, const float* Alo, const float* Bhi, const float* Blo, int M, int N, long long K,
+int launch_gemm(Handle* h, const float* A, const float* Bhi, const float* Blo, int M, int N, long long K,
                 int splits, const GemmParams& gp, cudaStream_t st) {
-    CUtensorMap mAhi, mAlo, mBhi, mBlo;
-    PB_TRY(make_map(h, &mAhi, Ahi, M, K, BM));
-    PB_TRY(make_map(h, &mAlo, Alo, M, K, BM));
+    CUtensorMap mAhi, mBhi, mBlo;
+    PB_TRY(make_map(h, &mAhi, A, M, K, BM));
     PB_TRY(make_map(h, &mBhi, Bhi, N, K, BN));
     PB_TRY(make_map(h, &mBlo, Blo, N, K, BN));
     if (attr_needed(h, reinterpret_cast<const void*>(tc_gemm_kernel)))
         PB_CUDA(h, cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     dim3 grid(M / BM, N / BN, splits);
-    tc_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mAhi, mAlo, mBhi, mBlo, gp);
+    tc_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mAhi, mBhi, mBlo, gp);
     PB_LAUNCH_CHECK(h);
     return PB_OK;
 }
@@ -381,10 +391,10 @@ extern "C" int pb_mdft_tc_expand(pb_handle_t hh, const void* E, int m, int n, vo
 }
 
 extern "C" long long pb_mdft_tc_work_bytes(int my, int ny, int mx, int nx) {
-    const long long a_lo = 2LL * ny * nx * 4;                // lo part of the data
-    const long long t1 = 2LL * (2LL * ny * mx) * 4;          // T1^T hi + lo (complex mx x ny each)
+    (void)nx;
+    const long long t1 = 2LL * ny * mx * 4;                   // T1^T (complex mx x ny)
     const long long ws = (long long)pick_splits(ny) * 2 * my * mx * 4;
-    return a_lo + t1 + ws + 4096;
+    return t1 + ws + 4096;
 }
 
 extern "C" int pb_mdft_tc_apply(pb_handle_t hh, const void* ExB_hi, const void* ExB_lo, const void* EyB_hi,
@@ -401,24 +411,16 @@ extern "C" int pb_mdft_tc_apply(pb_handle_t hh, const void* ExB_hi, const void* 
     // 2 K-blocks (8 main accumulation steps) per drain: < 1e-6 of the fp64 result at any K (measured:
     // 16 -> 2e-6, 8 -> 1.5e-6, 4 -> 1.2e-6, 2 -> 9e-7 on random data; the drains hide behind the L2-bound mainloop)
     static const int chunk = [] { const char* e = getenv("PB_MDFT_CHUNK"); return e ? std::max(1, atoi(e)) : 2; }();
-    float* a_lo = reinterpret_cast<float*>(work);
-    float* t1_hi = a_lo + 2LL * ny * nx;
-    float* t1_lo = t1_hi + 2LL * ny * mx;
-    float* ws = t1_lo + 2LL * ny * mx;
-
-    {   // lo part of the data under the TF32 split
-        const long long n4 = 2LL * ny * nx / 4;
-        const int g = (int)std::min<long long>((n4 + 255) / 256, (long long)h->sm_count * 16);
-        split_lo_kernel<<<g, 256, 0, st>>>((const float4*)a, (float4*)a_lo, n4);
-        PB_LAUNCH_CHECK(h);
-    }
+    static const int conv_b = [] { const char* e = getenv("PB_MDFT_CONV_B"); return e ? atoi(e) : 0; }();
+    float* t1 = reinterpret_cast<float*>(work);
+    float* ws = t1 + 2LL * ny * mx;
     {   // stage 1: T1^T(mx, ny) = (a @ Ex^T)^T : M = ny rows of a, N = 2*mx expanded basis rows, K = 2*nx
-        GemmParams gp{(int)(2LL * nx / BK), chunk, 0, t1_hi, t1_lo, (long long)ny, 0};
-        PB_TRY(launch_gemm(h, (const float*)a, a_lo, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
+        GemmParams gp{(int)(2LL * nx / BK), chunk, 0, conv_b, t1, nullptr, (long long)ny, 0};
+        PB_TRY(launch_gemm(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
     }
     {   // stage 2: out^T' = T1^T' @ Ey'^T : M = mx, N = 2*my, K = 2*ny, split-K partials transposed into ws[s][2my][mx]
-        GemmParams gp{(int)(2LL * ny / BK / splits), chunk, 1, ws, nullptr, (long long)mx, 2LL * my * mx};
-        PB_TRY(launch_gemm(h, t1_hi, t1_lo, (const float*)EyB_hi, (const float*)EyB_lo, mx, 2 * my, 2LL * ny, splits, gp, st));
+        GemmParams gp{(int)(2LL * ny / BK / splits), chunk, 1, conv_b, ws, nullptr, (long long)mx, 2LL * my * mx};
+        PB_TRY(launch_gemm(h, t1, (const float*)EyB_hi, (const float*)EyB_lo, mx, 2 * my, 2LL * ny, splits, gp, st));
     }
     {
         const long long tot = (long long)my * mx;

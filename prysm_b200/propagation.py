@@ -147,15 +147,17 @@ def angular_spectrum_transfer_function(samples, wvl, dx, z):
     return _ops.mul_outer(ones, vy=ty, vx=tx)
 
 
-def angular_spectrum(field, wvl, dx, z, Q=2, tf=None):
+def angular_spectrum(field, wvl, dx, z, Q=2, tf=None, screen=None):
     """ifft2(fft2(pad(field)) * tf) in one call; the padded result is returned un-cropped
-    (prysm/propagation/angular_spectrum.py:9-42)."""
+    (prysm/propagation/angular_spectrum.py:9-42).  `screen` (an extension): a complex array the field is multiplied
+    by inside the first transform pass -- `angular_spectrum(w, ..., screen=s)` == `angular_spectrum(w * s, ...)`."""
     f = _field(field)
+    scr = None if screen is None else _field(screen)
     if tf is not None:
-        return _ops.angular_spectrum(f, tuple(f.shape), tf=_ops.asdevice(tf))
+        return _ops.angular_spectrum(f, tuple(f.shape), tf=_ops.asdevice(tf), screen=scr)
     k = _padded_shape(f.shape, Q)
     ty, tx = _ops.angular_spectrum_vectors(k, wvl, dx, z, f.dtype, f.device)
-    return _ops.angular_spectrum(f, k, ty=ty, tx=tx)
+    return _ops.angular_spectrum(f, k, ty=ty, tx=tx, screen=scr)
 
 
 def angular_spectrum_adjoint(field, wvl, dx, z, Q=2, tf=None):
@@ -335,6 +337,7 @@ class Wavefront:
     def __init__(self, cmplx_field, wavelength, dx, space='pupil'):
         self._data = None if cmplx_field is None else _ops.asdevice(cmplx_field)
         self._lazy = None
+        self._lazy_mul = None    # (field, screen): a pending elementwise product that free_space() can fuse
         self.wavelength = wavelength
         self.dx = dx
         self.space = space
@@ -345,12 +348,17 @@ class Wavefront:
         if self._data is None and self._lazy is not None:
             amp, opd = self._lazy
             self._data = _ops.phase_screen(amp, opd, phase_prefix(self.wavelength).imag)
+        elif self._data is None and self._lazy_mul is not None:
+            a, b = self._lazy_mul
+            self._data = _ops.binary('mul', a, b)
+            self._lazy_mul = None
         return self._data
 
     @data.setter
     def data(self, value):
         self._data = value
         self._lazy = None
+        self._lazy_mul = None
 
     @classmethod
     def from_amp_and_phase(cls, amplitude, phase, wavelength, dx):
@@ -467,9 +475,18 @@ class Wavefront:
             ]
             if not all(criteria):
                 raise ValueError('all physicality criteria not met: sample spacing, shape, wavelength, or space different.')
+            if op == 'mul':   # kept pending: `(wf * screen).free_space(dz)` multiplies inside the first transform pass
+                out = Wavefront(None, self.wavelength, self.dx, self.space)
+                out._lazy_mul = (self.data, _ops.ascomplex(other.data).to(self.data.dtype))
+                return out
             data = _ops.binary(op, self.data, other.data, reverse)
         elif isinstance(other, (torch.Tensor, np.ndarray)):      # host arrays are uploaded like everywhere else
-            data = _ops.binary(op, self.data, _ops.asdevice(other), reverse)
+            od = _ops.asdevice(other)
+            if op == 'mul' and tuple(od.shape) == tuple(self.data.shape):
+                out = Wavefront(None, self.wavelength, self.dx, self.space)
+                out._lazy_mul = (self.data, _ops.ascomplex(od).to(self.data.dtype))
+                return out
+            data = _ops.binary(op, self.data, od, reverse)
         elif isinstance(other, numbers.Number):
             data = _ops.binary(op, self.data, other, reverse)
         else:
@@ -504,7 +521,11 @@ class Wavefront:
         """Plane-to-plane propagation (prysm/propagation/wavefront.py:413-443)."""
         if np.isnan(dz) and tf is None:
             raise ValueError('dz must be provided if tf is None')
-        out = angular_spectrum(self.data, wvl=self.wavelength, dx=self.dx, z=dz, Q=Q, tf=tf)
+        if self._data is None and self._lazy_mul is not None:     # pending wf * screen: fused into the first pass
+            a, b = self._lazy_mul
+            out = angular_spectrum(a, wvl=self.wavelength, dx=self.dx, z=dz, Q=Q, tf=tf, screen=b)
+        else:
+            out = angular_spectrum(self.data, wvl=self.wavelength, dx=self.dx, z=dz, Q=Q, tf=tf)
         return Wavefront(out, self.wavelength, self.dx, self.space)
 
     def free_space_adjoint(self, dz=np.nan, Q=1, tf=None):
@@ -555,6 +576,8 @@ class Wavefront:
     def _shape(self):
         if self._data is None and self._lazy is not None:
             return tuple(self._lazy[1].shape)
+        if self._data is None and self._lazy_mul is not None:
+            return tuple(self._lazy_mul[0].shape)
         return tuple(self.data.shape)
 
     def prepare_executor(self, efl, dx, samples, shift=(0, 0), kind='mdft'):
