@@ -33,14 +33,23 @@ def crand(rng, shape):
     return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
 
 
-def ref_pupil(N):
-    """SURVEY.md 8(d) builder, executed by the reference's own code in fp64."""
+def ref_pupil(N, round32=False):
+    """SURVEY.md 8(d) builder, executed by the reference's own code in fp64.  round32: the OPD is rounded to float32
+    once (and handed on as fp64), so that the fp64 reference run and a complex64 run start from bit-identical values
+    and their difference is transform error, not input rounding."""
     x, y = make_xy_grid(N, diameter=10.0)
     r, t = cart_to_polar(x, y)
     amp = circle(5.0, r)
     nms = [noll_to_nm(j) for j in range(2, 38)]
     coefs = np.random.default_rng(20260923).normal(0, 30.0, 36)
-    opd = sum_of_2d_modes(zernike_nm_seq(nms, r / 5.0, t), coefs)
+    # mode by mode in a fixed order (opd += c_j * Z_j): the summation order of a tensordot is an implementation detail, a
+    # loop of IEEE multiply-adds is not -- the fp32-rounded OPD below must be reproducible bit for bit by the tests
+    opd = np.zeros((N, N))
+    for idx in np.array_split(np.arange(36), 6):      # bounded memory at 4096^2
+        for z, c in zip(zernike_nm_seq([nms[i] for i in idx], r / 5.0, t), coefs[idx]):
+            opd += c * z
+    if round32:
+        opd = opd.astype(np.float32).astype(np.float64)
     return amp, opd, 10.0 / N
 
 
@@ -133,7 +142,7 @@ def window(a, w):
 def full():
     # C1: 256^2 -> 512^2 fp64 FFT focus;  C2: 2048^2 -> 4096^2 (fp64 arbiter for the fp32 GPU path)
     for name, N in (('c1', 256), ('c2', 2048)):
-        amp, opd, dx = ref_pupil(N)
+        amp, opd, dx = ref_pupil(N, round32=(name != 'c1'))
         wf = Wavefront.from_amp_and_phase(amp, opd, HeNe, dx)
         ps = wf.focus(100.0, Q=2)
         I = ps.intensity.data
@@ -149,7 +158,7 @@ def full():
         print(f'full_{name}.npz written; I_max={I.max():.6e}')
     # C3: 4096^2 -> 512^2 MDFT (focal_dx = wvl*F#/4)
     N = 4096
-    amp, opd, dx = ref_pupil(N)
+    amp, opd, dx = ref_pupil(N, round32=True)
     wf = Wavefront.from_amp_and_phase(amp, opd, HeNe, dx)
     fdx = HeNe * (100.0 / 10.0) / 4
     ex = wf.prepare_executor(100.0, fdx, 512, kind='mdft')
@@ -166,7 +175,7 @@ def full_c45():
     """BASELINE configs C4 (2048^2 x wavelengths, CZT -> 2048^2) and C5 (4096^2 free-space plane with a phase screen):
     windows / strided samples / sums of the reference's fp64 outputs -> full_c4.npz, full_c5.npz."""
     N = M = 2048
-    amp, opd, dx = ref_pupil(N)
+    amp, opd, dx = ref_pupil(N, round32=True)
     g = dict(N=np.int64(N), M=np.int64(M), focal_dx=np.float64(2.5), efl=np.float64(100.0))
     tot = 0
     for w, wt in ((0.5, 0.25), (0.7, 0.75)):
@@ -182,14 +191,21 @@ def full_c45():
     np.savez_compressed(os.path.join(OUT, 'full_c4.npz'), **g)
     print('full_c4.npz written')
     N = 4096
-    amp, opd, dx = ref_pupil(N)
+    amp, opd, dx = ref_pupil(N, round32=True)
     wf = Wavefront.from_amp_and_phase(amp, opd, HeNe, dx)
-    phi = np.random.default_rng(1000).normal(0, 0.1, (N, N))
-    scr = Wavefront(np.exp(1j * phi), HeNe, dx)
-    out = (wf * scr).free_space(dz=5.0, Q=1).data
+    # the screen exp(i phi), phi ~ N(0, 0.1 rad), expressed as an OPD in nm and rounded to float32 once (see ref_pupil)
+    phi32 = np.random.default_rng(1000).normal(0, 0.1, (N, N)).astype(np.float32)
+    scr_opd = (phi32.astype(np.float64) * (HeNe * 1e3 / (2 * np.pi))).astype(np.float32).astype(np.float64)
+    scr = Wavefront.phase_screen(scr_opd, HeNe, dx)
+    plane = (wf * scr).free_space(dz=5.0, Q=1)
+    out = plane.data
+    fdx = HeNe * (100.0 / 10.0) / 4
+    foc = plane.focus_dft(plane.prepare_executor(100.0, fdx, 512, kind='czt')).data      # the chain's final CZT focus
     g = dict(N=np.int64(N), dz=np.float64(5.0), field_win=window(out, 64), field_stride=out[::128, ::128],
              absmax=np.float64(np.abs(out).max()), E_out=np.float64((np.abs(out) ** 2).sum()),
-             E_in=np.float64((np.abs(wf.data) ** 2).sum()), edge=out[N // 2, 1000:1100])
+             E_in=np.float64((np.abs(wf.data) ** 2).sum()), edge=out[N // 2, 1000:1100],
+             focal_dx=np.float64(fdx), focus_win=window(foc, 64), focus_stride=foc[::16, ::16],
+             focus_absmax=np.float64(np.abs(foc).max()), focus_I_sum=np.float64((np.abs(foc) ** 2).sum()))
     np.savez_compressed(os.path.join(OUT, 'full_c5.npz'), **g)
     print('full_c5.npz written')
 

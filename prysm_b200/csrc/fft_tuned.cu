@@ -209,6 +209,9 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {   // into L2 only
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void st_hint(float4* p, float4 v, uint64_t pol) {
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
@@ -491,9 +494,9 @@ template <int L> struct Geo2 {
 //     warp instruction.  The groups drift apart by up to one tile, so the exchange phases of one overlap the butterfly
 //     phases of the other (the v1 column kernel ran one 16-warp line group in lock step: FP32 pipe 25 %).
 //   * the 4-column x L-row input tile (64 KB) is gathered ONCE for both halves by tensor TMA (box = 4 columns x 256
-//     rows) into a staging area of its own; thread 0 requests tile i+1 at the first of its barriers after all 16 warps
-//     have the inputs of tile i in registers (a non-blocking mbarrier test at every barrier of group 0) -- most of a
-//     tile time of lead (the gather of 2048 32-byte runs takes ~2-3 us).
+//     rows) into a staging area of its own; the last of the 16 warps to have the inputs of tile i in registers (a
+//     shared-memory counter) requests tile i+1 on the spot -- most of a tile time of lead (the gather of 2048 32-byte
+//     runs takes ~2-3 us).
 //   * one twiddle plan for both halves (float2 entries, 17 KB): half 1's stage-1 twiddles are the plan's times the
 //     per-thread constant w_2L^t (its input ramp x w_K^n = x w_32^(n/NT) w_2L^t; the w_32 part is a compile-time constant).
 template <int L> struct Geo4 {
@@ -565,16 +568,22 @@ __device__ __forceinline__ void focus_col4_group(const CUtensorMap& in_map, cons
     const float2* __restrict__ plan = reinterpret_cast<const float2*>(smem4 + G4::PLAN2);
     float4* S = smem4 + (HALF * 2 + cp) * G4::XBUF;
     const SyncGroup gsync{1 + HALF, 2 * NT};
-    const uint64_t pol_tmp = l2_policy(p.hints ? 2 : 0), pol_in = l2_policy(p.hints ? 1 : 0);
-    const bool issuer = HALF == 0 && lt == 0;
+    const uint64_t pol_tmp = l2_policy((p.hints & 1) ? 2 : 0), pol_in = l2_policy((p.hints & 1) ? 1 : 0);
     auto request_tile = [&](int ww) {   // one thread: gather tile ww = (field, column tile) into the staging area
         const int fb = ww / G2::TILES, tile = ww - fb * G2::TILES;
         mbar_expect_tx(bar + 1, (uint32_t)(L * 4 * sizeof(float2)));
 #pragma unroll
         for (int b = 0; b < G2::NBOX_IN; ++b)
             tma_load_3d(smem4 + G4::STAGE + b * G2::BOXR * 2, &in_map, tile * 4, b * G2::BOXR, fb, bar + 1, pol_in);
+        const int nn = ww + gridDim.x;   // the tile after: pull it from HBM into L2 now, so that its gather is an L2 hit
+        if ((p.hints & 2) && nn < p.ntiles) {
+            const int fb2 = nn / G2::TILES, tile2 = nn - fb2 * G2::TILES;
+#pragma unroll
+            for (int b = 0; b < G2::NBOX_IN; ++b) tma_prefetch_3d(&in_map, tile2 * 4, b * G2::BOXR, fb2);
+        }
     };
-    if (issuer) {
+    unsigned int* released = reinterpret_cast<unsigned int*>(bar + 2);   // warps that hold the inputs of the current tile, summed over tiles
+    if (HALF == 0 && lt == 0) {
         mbar_expect_tx(bar, (uint32_t)(G4::PLANLEN * sizeof(float2)));
         bulk_g2s(smem4 + G4::PLAN2, p.plan, (uint32_t)(G4::PLANLEN * sizeof(float2)), bar);
         if ((int)blockIdx.x < p.ntiles) request_tile(blockIdx.x);
@@ -586,16 +595,7 @@ __device__ __forceinline__ void focus_col4_group(const CUtensorMap& in_map, cons
     int it = 0;
     for (int w = blockIdx.x; w < p.ntiles; w += gridDim.x, ++it) {
         const int fb = w / G2::TILES, tile = w - fb * G2::TILES;
-        bool pending = issuer && w + (int)gridDim.x < p.ntiles;   // the next tile exists and has not been requested
-        auto poll = [&](bool block) {   // request the next tile once every warp has released the staging area
-            if (!pending) return;
-            if (block) mbar_wait(bar + 2, it & 1);
-            else if (!mbar_test(bar + 2, it & 1)) return;
-            fence_proxy_async();
-            request_tile(w + gridDim.x);
-            pending = false;
-        };
-        auto sync = [&]() { gsync(); poll(false); };
+        auto sync = [&]() { gsync(); };
         P2 v[16];
         {
             float4 x[16];   // (col, col + 1) x (re, im)
@@ -614,7 +614,15 @@ __device__ __forceinline__ void focus_col4_group(const CUtensorMap& in_map, cons
             PB_LANES2(8) PB_LANES2(9) PB_LANES2(10) PB_LANES2(11) PB_LANES2(12) PB_LANES2(13) PB_LANES2(14) PB_LANES2(15)
 #undef PB_LANES2
             __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(bar + 2);   // this warp holds its inputs: one of 16 releases of the staging area
+            if ((threadIdx.x & 31) == 0) {   // this warp holds its inputs: one of 16 releases of the staging area per tile;
+                __threadfence_block();       // the LAST warp to release it requests the next tile on the spot
+                const unsigned int n = atomicAdd(released, 1u) + 1u;
+                __threadfence_block();
+                if (n == (unsigned int)(it + 1) * (4 * NT / 32) && w + (int)gridDim.x < p.ntiles) {
+                    fence_proxy_async();
+                    request_tile(w + gridDim.x);
+                }
+            }
         }
         fft_two_stages_u<L, INV, HALF>(v, t, S, plan + G4::TW1, plan + G4::TW2, u, sync);
         fft_last_stage_load<L, INV>(v, t, S);
@@ -637,7 +645,6 @@ __device__ __forceinline__ void focus_col4_group(const CUtensorMap& in_map, cons
                              : make_float4(-sgn * y.im.x, sgn * y.re.x, -sgn * y.im.y, sgn * y.re.y);
                 st_hint(dst + o, q, pol_tmp);
             }
-        poll(true);
     }
 }
 
@@ -651,7 +658,7 @@ __global__ void __launch_bounds__(Geo4<L>::THREADS) focus_col4_kernel(const __gr
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_init(bar + 1, 1);
-        mbar_init(bar + 2, 4 * G::NT / 32);   // one arrival per compute warp
+        *reinterpret_cast<unsigned int*>(bar + 2) = 0u;   // release counter of the staging area
         mbar_fence_init();
     }
     __syncthreads();
@@ -672,7 +679,7 @@ __global__ void __launch_bounds__(L / 16) focus_row2_kernel(const __grid_constan
     uint64_t* bar = reinterpret_cast<uint64_t*>(inb + L);        // 1 mbarrier
     const int t = threadIdx.x;
     int r = blockIdx.x;
-    const uint64_t pol_tmp = l2_policy(p.hints ? 1 : 0), pol_out = l2_policy(p.hints ? 1 : 0);
+    const uint64_t pol_tmp = l2_policy((p.hints & 1) ? 1 : 0), pol_out = l2_policy((p.hints & 1) ? 1 : 0);
     auto request_row = [&](int R) {   // one thread: gather intermediate row R = (field, plane, j) into `inb`
         const int fb = R / (2 * L), rf = R - fb * (2 * L);
         const int ph = rf / L, j = rf - ph * L;
@@ -773,7 +780,7 @@ __global__ void __launch_bounds__(4 * L / 16) focus_row4_kernel(const __grid_con
     const float2* __restrict__ plan = reinterpret_cast<const float2*>(smraw + R4::PLAN_OFF);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + R4::BAR_OFF);   // [0] plan, [1 + grp] row of group grp
     uint64_t* bar = bars + 1 + grp;
-    const uint64_t pol_tmp = l2_policy(p.hints ? 1 : 0), pol_out = l2_policy(p.hints ? 1 : 0);
+    const uint64_t pol_tmp = l2_policy((p.hints & 1) ? 1 : 0), pol_out = l2_policy((p.hints & 1) ? 1 : 0);
     auto request_row = [&](int R) {   // one thread: gather intermediate row R = (field, plane, j) into `inb`
         const int fb = R / (2 * L), rf = R - fb * (2 * L);
         const int ph = rf / L, j = rf - ph * L;
@@ -1024,7 +1031,7 @@ int launch_focus2(Handle* h, FocusParams p, int batch, cudaStream_t st) {
     PB_TRY(get_col4_plan<L>(h, &plan_col));
     p.nrows = batch * 2 * L;
     p.ntiles = batch * G2::TILES;
-    static const int hints = env_int("PB_FOCUS_L2_HINTS", 1);
+    static const int hints = env_int("PB_FOCUS_L2_HINTS", 1);   // bit 0: eviction hints, bit 1: L2 prefetch of the tile after next
     p.hints = hints;
     const CUtensorMap *in_map = nullptr, *tmp_map = nullptr;
     {   // intermediate: [group = (field, plane, j/4)][tile][j%4][c]
@@ -1067,7 +1074,7 @@ __device__ __forceinline__ float2 cmul_s(float2 a, float2 b, int conj) {
 }
 
 template <int L, bool INV, bool COLS, int TP, bool RT, bool PM>
-__global__ void __launch_bounds__((COLS ? TP : 1) * L / 16) axis_reg_kernel(const AxisPass p, const float2* __restrict__ tw1,
+__global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && !COLS && L >= 4096) ? 2 : 0) axis_reg_kernel(const AxisPass p, const float2* __restrict__ tw1,
                                                                             const float2* __restrict__ tw2) {
     using G = Geo<L>;
     constexpr int NT = G::NT;
@@ -1124,7 +1131,9 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16) axis_reg_kernel(cons
             }
         }
     }
-    float4* S = smem4 + c * (G::SBUF + 2);
+    // TP interleaved lines per CTA: consecutive exchange buffers are offset by 32 / TP banks (8 / TP float4 of padding), so
+    // that the 8 threads of a 128-bit wavefront (8 / TP consecutive t  x  TP lines) cover all 32 banks
+    float4* S = smem4 + c * (G::SBUF + 8 / (COLS ? TP : 1) % 8);
     fft_two_stages<L, INV, 2>(v, t, S, tw1, tw2, SyncCta(), SyncCta());
     fft_last_stage_load<L, INV>(v, t, S);
 #pragma unroll
@@ -1229,7 +1238,7 @@ template <int L, bool INV, bool COLS, bool RT, bool PM = false>
 int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     using G = Geo<L>;
     constexpr int TP = COLS ? (L >= 4096 ? 2 : 2) : 1;
-    const size_t smem = (size_t)TP * (G::SBUF + 2) * sizeof(float4);
+    const size_t smem = (size_t)TP * (G::SBUF + 8 / TP % 8) * sizeof(float4);
     if (attr_needed(h, reinterpret_cast<const void*>(axis_reg_kernel<L, INV, COLS, TP, RT, PM>))) {
         PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // keep >= 64 KB of L1 for the twiddle tables (see launch_focus)

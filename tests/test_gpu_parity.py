@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import prysm_oracle as O
-from conftest import rel_linf, load_golden
+from conftest import rel_linf, load_golden, within
 
 pytestmark = pytest.mark.gpu
 
@@ -222,13 +222,13 @@ def test_executors_vs_reference_golden(pb, small, i, kind, prec):
     P = pb.propagation
     pb.config.precision = prec
     cdt = np.complex128 if prec == 64 else np.complex64
-    tol = TOL64 if prec == 64 else 2 * TOL32
+    tol = TOL64 if prec == 64 else TOL32
     a, g = small[f'ex{i}_in'].astype(cdt), small[f'ex{i}_gin'].astype(cdt)
     pdx, fdx, wvl, efl, sx, sy = (float(v) for v in small[f'ex{i}_params'])
     ex = P.prepare_executor(pdx, a.shape, fdx, g.shape, wvl, efl, (sx, sy), kind)
     assert ex.pupil_dx == pdx and ex.focal_dx == fdx
-    assert rel_linf(host(ex(a)), small[f'ex{i}_{kind}_fwd']) < tol
-    assert rel_linf(host(ex.adjoint(g)), small[f'ex{i}_{kind}_adj']) < tol
+    within(f'executors.{kind}{i}.p{prec}.fwd', rel_linf(host(ex(a)), small[f'ex{i}_{kind}_fwd']), tol)
+    within(f'executors.{kind}{i}.p{prec}.adj', rel_linf(host(ex.adjoint(g)), small[f'ex{i}_{kind}_adj']), tol)
     assert ex.nbytes() > 0
     pb.config.precision = 64
 
@@ -376,22 +376,23 @@ def test_c2_2048_focus_fp32_headline(pb):
     assert psf.dx == pytest.approx(float(g['psf_dx']), rel=1e-12)
     f = host(psf.data)
     amax = float(g['field_absmax'])
-    assert np.abs(_window(f, 64) - g['field_win']).max() / amax < TOL32
-    assert np.abs(f[::N // 16, ::N // 16] - g['field_stride']).max() / amax < TOL32
+    # bounds: the full-array figures of profiles/r02_parity.json (identical inputs; field 1.4e-7, PSF 2.3e-7) x 1.5
+    within('c2.field_window', np.abs(_window(f, 64) - g['field_win']).max() / amax, 2.1e-7)
+    within('c2.field_stride', np.abs(f[::N // 16, ::N // 16] - g['field_stride']).max() / amax, 2.1e-7)
     I = host(psf.intensity.data).astype(np.float64)
-    assert np.abs(_window(I, 64) - g['I_win']).max() / float(g['I_max']) < TOL32   # PSF relative L-inf
-    assert abs(I.sum() / float(g['E_in']) - 1) < 1e-6                              # energy conservation
-    assert np.abs(I.sum(axis=1)[::8] - g['I_rowsum']).max() / g['I_rowsum'].max() < 1e-6
-    assert np.abs(I.sum(axis=0)[::8] - g['I_colsum']).max() / g['I_colsum'].max() < 1e-6
+    within('c2.psf_window', np.abs(_window(I, 64) - g['I_win']).max() / float(g['I_max']), 3.5e-7)   # PSF relative L-inf
+    within('c2.energy', abs(I.sum() / float(g['E_in']) - 1), 5e-7)                                   # energy conservation
+    within('c2.rowsum', np.abs(I.sum(axis=1)[::8] - g['I_rowsum']).max() / g['I_rowsum'].max(), 5e-7)
+    within('c2.colsum', np.abs(I.sum(axis=0)[::8] - g['I_colsum']).max() / g['I_colsum'].max(), 5e-7)
     mtf = host(pb.otf.mtf_from_psf(psf.intensity).data)
-    assert np.abs(_window(mtf, 64) - g['mtf_win']).max() < 5e-6                    # MTF abs L-inf
-    assert np.abs(mtf[mtf.shape[0] // 2, ::8] - g['mtf_row']).max() < 5e-6
+    within('c2.mtf_window', np.abs(_window(mtf, 64) - g['mtf_win']).max(), 1e-6)                      # MTF abs L-inf
+    within('c2.mtf_row', np.abs(mtf[mtf.shape[0] // 2, ::8] - g['mtf_row']).max(), 1e-6)
     # fused synth -> focus -> |.|^2 gives the same PSF
     I2 = host(P.psf_from_amp_and_phase(amp, opd, HeNe, 2)).astype(np.float64)
-    assert np.abs(I2 - I).max() / float(g['I_max']) < TOL32
+    within('c2.fused_psf_vs_two_step', np.abs(I2 - I).max() / float(g['I_max']), 3.5e-7)
     # size-independent properties at full size: unitarity and linearity
     back = psf.unfocus(100.0, Q=1)
-    assert rel_linf(host(pb.fttools.crop_center(back.data, N)), host(field)) < 5e-6
+    within('c2.unfocus_round_trip', rel_linf(host(pb.fttools.crop_center(back.data, N)), host(field)), 1e-6)
     pb.config.precision = 64
 
 
@@ -409,13 +410,15 @@ def test_c3_4096_mdft_to_512(pb):
     f = host(out.data)
     amax = float(g['field_absmax'])
     assert f.shape == (M, M) and out.dx == float(g['focal_dx'])
-    assert np.abs(_window(f, 64) - g['field_win']).max() / amax < 2 * TOL32
-    assert np.abs(f[::16, ::16] - g['field_stride']).max() / amax < 2 * TOL32
+    # tensor-core MDFT (3xTF32): full-array field error 8.4e-7 with the reference's own fp32 run at 1.0e-6
+    # (profiles/r02_parity.json); the CZT of the same window: 3.0e-7
+    within('c3.mdft_field_window', np.abs(_window(f, 64) - g['field_win']).max() / amax, 1e-6)
+    within('c3.mdft_field_stride', np.abs(f[::16, ::16] - g['field_stride']).max() / amax, 1e-6)
     # CZT reaches the same answer (reference identity CZT == MDFT)
     ex2 = wf.prepare_executor(100.0, float(g['focal_dx']), M, kind='czt')
     f2 = host(wf.focus_dft(ex2).data)
-    assert np.abs(f2 - f).max() / amax < 3 * TOL32
-    assert np.abs(f2[::16, ::16] - g['field_stride']).max() / amax < 2 * TOL32
+    within('c3.czt_vs_mdft', np.abs(f2 - f).max() / amax, 1.2e-6)
+    within('c3.czt_field_stride', np.abs(f2[::16, ::16] - g['field_stride']).max() / amax, 4.5e-7)
     pb.config.precision = 64
 
 
@@ -438,7 +441,7 @@ def test_polychromatic_recipe_small(pb):
         ex = wf.prepare_executor(100.0, 2.5, M, kind='czt')
         planes.append(wf.focus_dft(ex).intensity.data)
     total = pb.polynomials.sum_of_2d_modes(torch.stack(planes), wts)
-    assert rel_linf(host(total), ref) < 2 * TOL32
+    within('polychromatic_small', rel_linf(host(total), ref), TOL32)
     pb.config.precision = 64
 
 
@@ -458,8 +461,8 @@ def test_mdft_tensor_core_path(pb, N, M):
     assert tc._tc is not None, 'tensor-core plan should cover this shape'
     simt = F.MDFT(x, x, f, f, -1, 0.5, use_tensor_cores=False)
     assert simt._tc is None
-    assert rel_linf(host(tc(a)), ref) < 1.5 * TOL32          # 3xTF32 + chunked fp32 accumulation
-    assert rel_linf(host(simt(a)), ref) < TOL32
+    within(f'mdft_tc.{N}_{M}', rel_linf(host(tc(a)), ref), TOL32)          # 3xTF32 + chunked fp32 accumulation
+    within(f'mdft_simt.{N}_{M}', rel_linf(host(simt(a)), ref), TOL32)
     # ragged shapes fall back to the CUDA-core GEMM
     assert F.MDFT(x[:100], x[:100], f[:50], f[:50])._tc is None
     pb.config.precision = 64

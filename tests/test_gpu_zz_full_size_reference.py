@@ -4,8 +4,14 @@ full_c5.npz: windows, strided samples, sums written by oracle/make_golden.py ful
   C4  2048^2 pupil -> CZT -> 2048^2 field at two wavelengths, weighted incoherent sum (polychromatic_psf)
   C5  4096^2 field x unit-modulus phase screen -> free_space(dz = 5 mm)
 
-Tolerance: relative L-inf (normalised by the reference's max) 2e-6 for the CZT fields (fp32 Bluestein),
-4e-6 for the free-space plane (three fp32 transforms of length 4096), sums 1e-5."""
+Inputs are bit-identical on both sides: the golden run used the OPD (and the screen's OPD) rounded to float32 once, which
+is exactly what the complex64 path is fed here, so the differences below are transform error only.
+Bounds = the full-array figures of profiles/r02_parity.json (same inputs, same kernels, the reference fp64 run as arbiter)
+times at most 1.5; every one is inside the north-star 1e-6:
+    C4 CZT fields        measured 2.9e-7 / 3.5e-7   bound 5.5e-7      (the reference's own fp32 run: 1.2e-4 / 4.0e-4)
+    C4 weighted PSF sum  measured 7.3e-7            bound 1.0e-6      (reference fp32: 2.2e-4)
+    C5 free-space plane  measured 6.7e-7            bound 1.0e-6      (reference fp32: 4.0e-6)
+    C5 final CZT focus   measured 4.3e-7            bound 6.5e-7      (reference fp32: 2.5e-5)"""
 import numpy as np
 import pytest
 import torch
@@ -43,16 +49,16 @@ def test_c4_czt_fields_and_incoherent_sum_vs_reference(pb):
         f = host(wf.focus_dft(wf.prepare_executor(100.0, 2.5, M, kind='czt')).data)
         den = float(g[tag + 'absmax'])
         assert f.shape == (M, M)
-        assert np.abs(f[::64, ::64] - g[tag + 'field_stride']).max() / den < 2e-6
-        assert np.abs(f[cy - 32:cy + 32, cy - 32:cy + 32] - g[tag + 'field_win']).max() / den < 2e-6
+        assert np.abs(f[::64, ::64] - g[tag + 'field_stride']).max() / den < 5.5e-7
+        assert np.abs(f[cy - 32:cy + 32, cy - 32:cy + 32] - g[tag + 'field_win']).max() / den < 5.5e-7
         I = (f.real.astype(np.float64) ** 2 + f.imag.astype(np.float64) ** 2).sum()
-        assert I == pytest.approx(float(g[tag + 'I_sum']), rel=1e-5)
+        assert I == pytest.approx(float(g[tag + 'I_sum']), rel=1e-6)
     from prysm_b200.polychromatic import polychromatic_psf
     tot = host(polychromatic_psf(amp, opd, [0.5, 0.7], [0.25, 0.75], dx, 100.0, 2.5, M, kind='czt')).astype(np.float64)
     smax = float(g['sum_max'])
-    assert np.abs(tot[::64, ::64] - g['sum_stride']).max() / smax < 2e-6
-    assert np.abs(tot[cy - 32:cy + 32, cy - 32:cy + 32] - g['sum_win']).max() / smax < 2e-6
-    assert tot.sum() == pytest.approx(float(g['sum_total']), rel=1e-5)
+    assert np.abs(tot[::64, ::64] - g['sum_stride']).max() / smax < 1e-6
+    assert np.abs(tot[cy - 32:cy + 32, cy - 32:cy + 32] - g['sum_win']).max() / smax < 1e-6
+    assert tot.sum() == pytest.approx(float(g['sum_total']), rel=1e-6)
 
 
 def test_c5_screen_and_free_space_plane_vs_reference(pb):
@@ -61,14 +67,23 @@ def test_c5_screen_and_free_space_plane_vs_reference(pb):
     N = 4096
     amp, opd, dx = O.synthetic_pupil(N, np.float32)
     wf = P.Wavefront.from_amp_and_phase(amp, opd, HeNe, dx)
-    phi = np.random.default_rng(1000).normal(0, 0.1, (N, N)).astype(np.float32)
-    scr = P.Wavefront.phase_screen(phi * (HeNe * 1e3 / (2 * np.pi)), HeNe, dx)       # exp(i*phi): OPD[nm] = phi*wvl/(2 pi)
-    out = host((wf * scr).free_space(dz=float(g['dz']), Q=1).data)
+    phi32 = np.random.default_rng(1000).normal(0, 0.1, (N, N)).astype(np.float32)
+    scr_opd = (phi32.astype(np.float64) * (HeNe * 1e3 / (2 * np.pi))).astype(np.float32)   # exp(i*phi): OPD[nm] = phi*wvl/(2 pi)
+    scr = P.Wavefront.phase_screen(scr_opd, HeNe, dx)
+    plane = (wf * scr).free_space(dz=float(g['dz']), Q=1)         # the screen multiply rides in the first transform pass
+    out = host(plane.data)
     den = float(g['absmax'])
     c = N // 2
     assert out.shape == (N, N)
-    assert np.abs(out[::128, ::128] - g['field_stride']).max() / den < 4e-6
-    assert np.abs(out[c - 32:c + 32, c - 32:c + 32] - g['field_win']).max() / den < 4e-6
-    assert np.abs(out[c, 1000:1100] - g['edge']).max() / den < 4e-6
+    assert np.abs(out[::128, ::128] - g['field_stride']).max() / den < 1e-6
+    assert np.abs(out[c - 32:c + 32, c - 32:c + 32] - g['field_win']).max() / den < 1e-6
+    assert np.abs(out[c, 1000:1100] - g['edge']).max() / den < 1e-6
     E = (out.real.astype(np.float64) ** 2 + out.imag.astype(np.float64) ** 2).sum()
-    assert E == pytest.approx(float(g['E_out']), rel=1e-5)
+    assert E == pytest.approx(float(g['E_out']), rel=1e-6)
+    # the chain's final focus: CZT 4096^2 -> 512^2
+    foc = host(plane.focus_dft(plane.prepare_executor(100.0, float(g['focal_dx']), 512, kind='czt')).data)
+    fden = float(g['focus_absmax'])
+    assert np.abs(foc[256 - 32:256 + 32, 256 - 32:256 + 32] - g['focus_win']).max() / fden < 6.5e-7
+    assert np.abs(foc[::16, ::16] - g['focus_stride']).max() / fden < 6.5e-7
+    If = (foc.real.astype(np.float64) ** 2 + foc.imag.astype(np.float64) ** 2).sum()
+    assert If == pytest.approx(float(g['focus_I_sum']), rel=2e-6)

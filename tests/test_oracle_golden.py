@@ -109,7 +109,8 @@ def test_c4_full_reference_samples():
     """BASELINE config C4 (2048^2 -> 2048^2 CZT per wavelength, weighted incoherent sum) against the reference's stored
     fp64 samples at two wavelengths."""
     g = load_golden('full_c4.npz')
-    amp, opd, dx = O.synthetic_pupil(2048, np.float64)
+    amp, opd, dx = O.synthetic_pupil(2048, np.float32)     # the golden inputs: OPD rounded to float32 once
+    opd = opd.astype(np.float64)
     tot = 0
     for w, wt in ((0.5, 0.25), (0.7, 0.75)):
         ex = O.prepare_executor(dx, (2048, 2048), 2.5, (2048, 2048), w, 100.0, kind='czt')
@@ -128,13 +129,18 @@ def test_c4_full_reference_samples():
 def test_c5_full_reference_samples():
     """BASELINE config C5: one 4096^2 plane -- screen multiply then free_space(dz = 5 mm) -- against the reference."""
     g = load_golden('full_c5.npz')
-    amp, opd, dx = O.synthetic_pupil(4096, np.float64)
-    field = O.from_amp_and_phase(amp, opd, HeNe)
-    phi = np.random.default_rng(1000).normal(0, 0.1, (4096, 4096))
-    out = O.angular_spectrum(field * np.exp(1j * phi), HeNe, dx, 5.0, 1)
+    amp, opd, dx = O.synthetic_pupil(4096, np.float32)     # the golden inputs: OPD and screen rounded to float32 once
+    field = O.from_amp_and_phase(amp, opd.astype(np.float64), HeNe)
+    phi32 = np.random.default_rng(1000).normal(0, 0.1, (4096, 4096)).astype(np.float32)
+    scr_opd = (phi32.astype(np.float64) * (HeNe * 1e3 / (2 * np.pi))).astype(np.float32).astype(np.float64)
+    out = O.angular_spectrum(field * O.phase_screen(scr_opd, HeNe), HeNe, dx, 5.0, 1)
     den = float(g['absmax'])
     assert np.abs(out[::128, ::128] - g['field_stride']).max() / den < 1e-9
     assert np.abs(out[2048 - 32:2048 + 32, 2048 - 32:2048 + 32] - g['field_win']).max() / den < 1e-9
     assert np.abs(out[2048, 1000:1100] - g['edge']).max() / den < 1e-9
     assert (np.abs(out) ** 2).sum() == pytest.approx(float(g['E_out']), rel=1e-10)
     assert float(g['E_out']) == pytest.approx(float(g['E_in']), rel=1e-10)        # |TF| = 1, |screen| = 1
+    foc = O.prepare_executor(dx, (4096, 4096), float(g['focal_dx']), (512, 512), HeNe, 100.0, kind='czt')(out)   # final CZT focus
+    fden = float(g['focus_absmax'])
+    assert np.abs(foc[256 - 32:256 + 32, 256 - 32:256 + 32] - g['focus_win']).max() / fden < 1e-9
+    assert np.abs(foc[::16, ::16] - g['focus_stride']).max() / fden < 1e-9

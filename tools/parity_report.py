@@ -101,7 +101,14 @@ def main():
     r64, r32 = ref_c2(64), ref_c2(32)
     g = gpu(lambda: P.Wavefront.from_amp_and_phase(amp, opd32, HENE, dx).focus(EFL, Q=2).data).cpu().numpy()
     I64 = np.abs(r64) ** 2
+    from prysm.otf import mtf_from_psf as ref_mtf
+    psf_dx = dx * 0 + HENE * EFL / (dx * 2 * N)
+    m64 = run_reference(64, lambda: ref_mtf(I64, psf_dx).data)
+    m32 = run_reference(32, lambda: ref_mtf((np.abs(r32.astype(np.complex128)) ** 2).astype(np.float32), psf_dx).data)
+    gm = gpu(lambda: pb.otf.mtf_from_psf(P.Wavefront.from_amp_and_phase(amp, opd32, HENE, dx).focus(EFL, Q=2).intensity).data).cpu().numpy()
+    mtf = {'gpu32_abs_linf': float(np.abs(gm - m64).max()), 'ref32_abs_linf': float(np.abs(m32 - m64).max())}
     rep['configs']['C2_fft_focus'] = {
+        'mtf_from_psf': mtf,
         'shape': [N, 2 * N], 'field': {'gpu32': metrics(g, r64), 'ref32': metrics(r32, r64)},
         'intensity': {'gpu32': metrics(np.abs(g.astype(np.complex128)) ** 2, I64), 'ref32': metrics(np.abs(r32.astype(np.complex128)) ** 2, I64)},
         'energy_conservation_gpu32': float((np.abs(g.astype(np.complex128)) ** 2).sum() / amp.sum() - 1)}
