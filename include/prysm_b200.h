@@ -122,6 +122,15 @@ int pb_czt_axis(pb_handle_t h, int dtype, const void* in, int ny, int nx, long l
                 const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj,
                 int out_off, int n_out, double scale, void* out, long long out_ld, void* stream);
 
+/* The same axis with the modulus fused into its store: out_kind = PB_OUT_INTENSITY writes |.|^2 (a REAL array),
+ * PB_OUT_ACCUMULATE adds weight * |.|^2 to it -- the last pass of one wavelength of an incoherent sum never writes its
+ * complex field.  Replaces the last axis of CZT.__call__ (prysm/fttools.py:296-325) followed by Wavefront.intensity
+ * (prysm/propagation/wavefront.py:147-151) and the running term of sum_of_2d_modes (prysm/polynomials/fitting.py:37). */
+int pb_czt_axis_intensity(pb_handle_t h, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int K,
+                          const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj,
+                          int out_off, int n_out, double scale, int out_kind, double weight, void* out,
+                          long long out_ld, void* stream);
+
 /* The Bluestein pieces of one CZT axis built on the device from scalars (no host maths, no uploads):
  * b (N), post = a*phase (M), H = FFT_K(h) (K), Hadj (K) as consumed by pb_czt_axis.  alpha = dx*dfx,
  * shift = f[M/2]/df, xc = x[N/2], f0 = f[0], df the frequency step.  prysm/fttools.py:257-291, 372-389 */

@@ -34,6 +34,7 @@ SIGNATURES = {
     'pb_axis_dft': (_i, [_vp, _i, _vp, _i, _i, _ll, _i, _i, _i, _d, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _ll, _vp]),
     'pb_czt_plan': (_i, [_vp, _i, _i, _i, _i, _d, _d, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     'pb_czt_axis': (_i, [_vp, _i, _vp, _i, _i, _ll, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _vp, _ll, _vp]),
+    'pb_czt_axis_intensity': (_i, [_vp, _i, _vp, _i, _i, _ll, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _i, _d, _vp, _ll, _vp]),
     'pb_angular_spectrum': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     'pb_angular_spectrum_screen': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     'pb_angular_spectrum_vectors': (_i, [_vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp]),

@@ -222,15 +222,31 @@ def czt_plan(N, M, K, shift, alpha, sign, xc, f0, df, cdtype, dev):
     return b, post, H, Hadj
 
 
-def czt_axis(a, K, axis, pre_e, H, post_e, out_off, n_out, scale=1.0, pre_conj=False, post_conj=False):
-    """pb_czt_axis: (a*pre_e) -> FFT_K -> *H -> IFFT_K -> [out_off:out_off+n_out] -> *post_e*scale along `axis`."""
-    a = ascomplex(a).contiguous()
+def czt_axis(a, K, axis, pre_e, H, post_e, out_off, n_out, scale=1.0, pre_conj=False, post_conj=False,
+             out_kind=capi.OUT_COMPLEX, weight=1.0, out=None):
+    """pb_czt_axis: (a*pre_e) -> FFT_K -> *H -> IFFT_K -> [out_off:out_off+n_out] -> *post_e*scale along `axis`.
+    `a` may be a row-pitched view (a column slice of a larger array): only unit column stride is required."""
+    a = ascomplex(a)
+    if a.stride(1) != 1 or a.stride(0) < a.shape[1]:
+        a = a.contiguous()
     ny, nx = a.shape
     axis = axis % 2
     oshape = (n_out, nx) if axis == 0 else (ny, n_out)
-    out = torch.empty(oshape, dtype=a.dtype, device=a.device)
     h, st = _ctx(a)
-    h.check(lib.pb_czt_axis(h.ptr, _CODE[a.dtype], _p(a), ny, nx, nx, axis, int(K), _p(pre_e), int(pre_conj), _p(H),
+    if out_kind != capi.OUT_COMPLEX:     # |.|^2 (written or accumulated with `weight`) formed in the pass's store
+        rd = _REAL_OF[a.dtype]
+        if out is None:
+            if out_kind == capi.OUT_ACCUMULATE:
+                raise ValueError('accumulate needs an existing `out` array')
+            out = torch.empty(oshape, dtype=rd, device=a.device)
+        else:
+            _check_out(out, oshape, rd, a.device)
+        h.check(lib.pb_czt_axis_intensity(h.ptr, _CODE[a.dtype], _p(a), ny, nx, a.stride(0), axis, int(K), _p(pre_e),
+                                          int(pre_conj), _p(H), _p(post_e), int(post_conj), int(out_off), int(n_out),
+                                          float(scale), int(out_kind), float(weight), _p(out), out.stride(0), st))
+        return out
+    out = torch.empty(oshape, dtype=a.dtype, device=a.device)
+    h.check(lib.pb_czt_axis(h.ptr, _CODE[a.dtype], _p(a), ny, nx, a.stride(0), axis, int(K), _p(pre_e), int(pre_conj), _p(H),
                             _p(post_e), int(post_conj), int(out_off), int(n_out), float(scale), _p(out), oshape[1], st))
     return out
 

@@ -285,10 +285,9 @@ extern "C" int pb_axis_dft(pb_handle_t hh, int dtype, const void* in, int ny, in
     return axis_dft(h, p, st);
 }
 
-extern "C" int pb_czt_axis(pb_handle_t hh, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int K,
-                           const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj, int out_off,
-                           int n_out, double scale, void* out, long long out_ld, void* stream) {
-    PB_ENTER(hh);
+static int czt_axis_impl(Handle* h, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int K,
+                         const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj, int out_off,
+                         int n_out, double scale, int out_kind, double weight, void* out, long long out_ld, void* stream) {
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");
     if (ny < 1 || nx < 1 || K < 1 || (axis != 0 && axis != 1) || !H) return fail(h, PB_ERR_INVALID, "bad czt arguments");
     if (out_off < 0 || n_out < 1 || out_off + n_out > K) return fail(h, PB_ERR_INVALID, "output window outside the transform");
@@ -304,6 +303,7 @@ extern "C" int pb_czt_axis(pb_handle_t hh, int dtype, const void* in, int ny, in
     if (axis == 1) { f.ibs = in_ld; f.ies = 1; f.obs = out_ld; f.oes = 1; f.batch_contiguous = 0; }
     else { f.ibs = 1; f.ies = in_ld; f.obs = 1; f.oes = out_ld; f.batch_contiguous = 1; }
     f.roundtrip = 1;
+    f.out_kind = out_kind; f.weight = weight;
     int rc = try_tuned_axis_pass(h, f, st);
     if (rc != PB_ERR_UNSUPPORTED) return rc;
     // two passes through a (lines x K) scratch
@@ -311,6 +311,7 @@ extern "C" int pb_czt_axis(pb_handle_t hh, int dtype, const void* in, int ny, in
     PB_TRY(ensure_scratch(h, 1, (size_t)nline * K * csize(dtype), &tmp));
     AxisPass a = f;
     a.roundtrip = 0; a.post_e2 = nullptr; a.out = tmp; a.n_out = K; a.crop_off = 0; a.scale = 1.0;
+    a.out_kind = PB_OUT_COMPLEX; a.weight = 1.0;
     if (axis == 1) { a.obs = K; a.oes = 1; } else { a.obs = 1; a.oes = nline; }
     PB_TRY(axis_dft(h, a, st));
     AxisPass b;
@@ -318,7 +319,26 @@ extern "C" int pb_czt_axis(pb_handle_t hh, int dtype, const void* in, int ny, in
     b.Llog = K; b.n_in = K; b.n_out = n_out; b.crop_off = out_off; b.nb = nline;
     b.post_e = post_e; b.post_e_conj = post_conj; b.post_off = out_off;
     b.ibs = a.obs; b.ies = a.oes; b.obs = f.obs; b.oes = f.oes; b.batch_contiguous = f.batch_contiguous;
+    b.out_kind = out_kind; b.weight = weight;
     return axis_dft(h, b, st);
+}
+
+extern "C" int pb_czt_axis(pb_handle_t hh, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int K,
+                           const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj, int out_off,
+                           int n_out, double scale, void* out, long long out_ld, void* stream) {
+    PB_ENTER(hh);
+    return czt_axis_impl(h, dtype, in, ny, nx, in_ld, axis, K, pre_e, pre_conj, H, post_e, post_conj, out_off, n_out, scale,
+                         PB_OUT_COMPLEX, 1.0, out, out_ld, stream);
+}
+
+extern "C" int pb_czt_axis_intensity(pb_handle_t hh, int dtype, const void* in, int ny, int nx, long long in_ld, int axis,
+                                     int K, const void* pre_e, int pre_conj, const void* H, const void* post_e,
+                                     int post_conj, int out_off, int n_out, double scale, int out_kind, double weight,
+                                     void* out, long long out_ld, void* stream) {
+    PB_ENTER(hh);
+    if (out_kind != PB_OUT_INTENSITY && out_kind != PB_OUT_ACCUMULATE) return fail(h, PB_ERR_INVALID, "out_kind must be intensity or accumulate");
+    return czt_axis_impl(h, dtype, in, ny, nx, in_ld, axis, K, pre_e, pre_conj, H, post_e, post_conj, out_off, n_out, scale,
+                         out_kind, weight, out, out_ld, stream);
 }
 
 static int angular_spectrum_impl(Handle* h, int dtype, const void* in, int ny, int nx, int ky, int kx, const void* ty,

@@ -1073,7 +1073,10 @@ __device__ __forceinline__ float2 cmul_s(float2 a, float2 b, int conj) {
                 : make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-template <int L, bool INV, bool COLS, int TP, bool RT, bool PM>
+// DENSE: the whole line is populated and kept -- no pad window, no rotation, no crop, an even number of lines, complex
+// input (free-space steps at Q = 1, plain transforms): the per-element window tests and index arithmetic of the general
+// form (about as many integer instructions as there are floating-point ones) compile away.
+template <int L, bool INV, bool COLS, int TP, bool RT, bool PM, bool DENSE>
 __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && !COLS && L >= 4096) ? 2 : 0) axis_reg_kernel(const AxisPass p, const float2* __restrict__ tw1,
                                                                             const float2* __restrict__ tw2) {
     using G = Geo<L>;
@@ -1081,7 +1084,7 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && !COLS && L >=
     extern __shared__ __align__(16) float4 smem4[];
     const int c = COLS ? threadIdx.x % TP : 0, t = COLS ? threadIdx.x / TP : threadIdx.x;
     const int b0 = (blockIdx.x * (COLS ? TP : 1) + c) * 2;   // lines b0 (lane A) and b0 + 1 (lane B)
-    const bool hasA = b0 < p.nb, hasB = b0 + 1 < p.nb;
+    const bool hasA = DENSE || b0 < p.nb, hasB = DENSE || b0 + 1 < p.nb;
     const float2* __restrict__ in = reinterpret_cast<const float2*>(p.in);
     const float2* __restrict__ pre_e = reinterpret_cast<const float2*>(p.pre_e);
     const float2* __restrict__ pre_b = reinterpret_cast<const float2*>(p.pre_b);
@@ -1091,13 +1094,16 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && !COLS && L >=
 #pragma unroll
     for (int n = 0; n < 16; ++n) {
         const int j = n * NT + t;
-        int pp = j + p.rot_in;
-        if (pp >= L) pp -= L;
-        const int li = pp - p.in_off;
+        int li = j;
+        if (!DENSE) {
+            int pp = j + p.rot_in;
+            if (pp >= L) pp -= L;
+            li = pp - p.in_off;
+        }
         float2 xa = make_float2(0.f, 0.f), xb = xa;
-        if (li >= 0 && li < p.n_in) {
+        if (DENSE || (li >= 0 && li < p.n_in)) {
             const long long o = (long long)b0 * p.ibs + (long long)li * p.ies;
-            if (p.in_kind == PB_IN_REAL) {   // real field (the PSF going to transform_psf): imaginary part 0
+            if (!DENSE && p.in_kind == PB_IN_REAL) {   // real field (the PSF going to transform_psf): imaginary part 0
                 const float* __restrict__ inr = reinterpret_cast<const float*>(p.in);
                 if (hasA) xa.x = __ldg(inr + o);
                 if (hasB) xb.x = __ldg(inr + o + p.ibs);
@@ -1118,10 +1124,13 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && !COLS && L >=
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
             const int j = n * NT + t;
-            int pp = j + p.rot_in;
-            if (pp >= L) pp -= L;
-            const int li = pp - p.in_off;
-            if (li >= 0 && li < p.n_in) {
+            int li = j;
+            if (!DENSE) {
+                int pp = j + p.rot_in;
+                if (pp >= L) pp -= L;
+                li = pp - p.in_off;
+            }
+            if (DENSE || (li >= 0 && li < p.n_in)) {
                 const long long om = (long long)b0 * p.pmi_bs + (long long)li * p.pmi_es;
                 float2 ma = make_float2(1.f, 0.f), mb = ma;
                 if (hasA) ma = ld_stream(pm + om);
@@ -1171,10 +1180,13 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && !COLS && L >=
 #pragma unroll
             for (int kk = 0; kk < G::R3; ++kk) {
                 const int j = t + g * NT + 256 * kk;
-                int q = j - p.crop_off + p.rot_out;
-                if (q < 0) q += L;
-                if (q >= L) q -= L;
-                if (q >= p.n_out) continue;
+                int q = j;
+                if (!DENSE) {
+                    q = j - p.crop_off + p.rot_out;
+                    if (q < 0) q += L;
+                    if (q >= L) q -= L;
+                    if (q >= p.n_out) continue;
+                }
                 const P2 y = w[g * G::R3 + kk];
                 float2 ya = make_float2(y.re.x, y.im.x), yb = make_float2(y.re.y, y.im.y);
                 if (p.post_e2) {  // final multiplier, indexed by the output sample (the CZT's a(m)*phase(m))
@@ -1182,8 +1194,20 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && !COLS && L >=
                     ya = cmul_s(ya, m, p.post_e2_conj); yb = cmul_s(yb, m, p.post_e2_conj);
                 }
                 const long long o = (long long)b0 * p.obs + (long long)q * p.oes;
-                if (hasA) st_stream(out + o, make_float2(ya.x * scale, ya.y * scale));
-                if (hasB) st_stream(out + o + p.obs, make_float2(yb.x * scale, yb.y * scale));
+                if (p.out_kind == PB_OUT_COMPLEX) {
+                    if (hasA) st_stream(out + o, make_float2(ya.x * scale, ya.y * scale));
+                    if (hasB) st_stream(out + o + p.obs, make_float2(yb.x * scale, yb.y * scale));
+                } else {   // |.|^2 (or weight * |.|^2 added to the plane): the complex field is never written
+                    float* __restrict__ outr = reinterpret_cast<float*>(p.out);
+                    const float s2 = scale * scale, wgt = (float)p.weight;
+                    float ia = s2 * fmaf(ya.x, ya.x, ya.y * ya.y), ib = s2 * fmaf(yb.x, yb.x, yb.y * yb.y);
+                    if (p.out_kind == PB_OUT_ACCUMULATE) {
+                        if (hasA) ia = fmaf(wgt, ia, outr[o]);
+                        if (hasB) ib = fmaf(wgt, ib, outr[o + p.obs]);
+                    }
+                    if (hasA) outr[o] = ia;
+                    if (hasB) outr[o + p.obs] = ib;
+                }
             }
         return;
     }
@@ -1192,10 +1216,13 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && !COLS && L >=
 #pragma unroll
         for (int kk = 0; kk < G::R3; ++kk) {
             const int k = t + g * NT + 256 * kk;
-            int q = k - p.crop_off + p.rot_out;
-            if (q < 0) q += L;
-            if (q >= L) q -= L;
-            if (q >= p.n_out) continue;
+            int q = k;
+            if (!DENSE) {
+                q = k - p.crop_off + p.rot_out;
+                if (q < 0) q += L;
+                if (q >= L) q -= L;
+                if (q >= p.n_out) continue;
+            }
             const P2 y = v[g * G::R3 + kk];
             float2 ya = make_float2(y.re.x, y.im.x), yb = make_float2(y.re.y, y.im.y);
             if (post_e) { const float2 w = post_e[k - p.post_off]; ya = cmul_s(ya, w, p.post_e_conj); yb = cmul_s(yb, w, p.post_e_conj); }
@@ -1234,24 +1261,24 @@ int get_plain_plan(Handle* h, const float2** tw1, const float2** tw2) {
     return PB_OK;
 }
 
-template <int L, bool INV, bool COLS, bool RT, bool PM = false>
+template <int L, bool INV, bool COLS, bool RT, bool PM = false, bool DENSE = false>
 int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     using G = Geo<L>;
     constexpr int TP = COLS ? (L >= 4096 ? 2 : 2) : 1;
     const size_t smem = (size_t)TP * (G::SBUF + 8 / TP % 8) * sizeof(float4);
-    if (attr_needed(h, reinterpret_cast<const void*>(axis_reg_kernel<L, INV, COLS, TP, RT, PM>))) {
-        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (attr_needed(h, reinterpret_cast<const void*>(axis_reg_kernel<L, INV, COLS, TP, RT, PM, DENSE>))) {
+        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT, PM, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // keep >= 64 KB of L1 for the twiddle tables (see launch_focus)
         const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
         const int ctas = std::max<int>(1, (int)((unified - l1_keep) / (smem + 1024)));
         const int pct = (int)std::min<size_t>(100, ((size_t)ctas * (smem + 1024) * 100 + h->max_smem_optin - 1) / h->max_smem_optin);
-        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT, PM>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        PB_CUDA(h, cudaFuncSetAttribute(axis_reg_kernel<L, INV, COLS, TP, RT, PM, DENSE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     const float2 *tw1 = nullptr, *tw2 = nullptr;
     PB_TRY(get_plain_plan<L>(h, &tw1, &tw2));
     const int lines_per_cta = 2 * TP;
     const int grid = (p.nb + lines_per_cta - 1) / lines_per_cta;
-    axis_reg_kernel<L, INV, COLS, TP, RT, PM><<<grid, TP * G::NT, smem, st>>>(p, tw1, tw2);
+    axis_reg_kernel<L, INV, COLS, TP, RT, PM, DENSE><<<grid, TP * G::NT, smem, st>>>(p, tw1, tw2);
     PB_LAUNCH_CHECK(h);
     return PB_OK;
 }
@@ -1259,9 +1286,23 @@ int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
 template <int L>
 int dispatch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     const bool cols = p.batch_contiguous != 0;
+    // the whole line populated and kept, lines in pairs, complex in: the index logic of the general kernel compiles away
+    const bool dense = p.rot_in == 0 && p.in_off == 0 && p.n_in == L && p.crop_off == 0 && p.rot_out == 0 && p.n_out == L &&
+                       !(p.nb & 1) && p.in_kind == PB_IN_COMPLEX && !p.post_e2 && p.pre_off == 0 && p.post_off == 0 &&
+                       (!cols || !(p.nb & 3));
     if (p.pre_mat) {   // the screened first pass of a free-space step: rows, plain transform
         if (cols || p.roundtrip) return PB_ERR_UNSUPPORTED;
+        if (dense) return p.dir < 0 ? launch_axis_reg<L, false, false, false, true, true>(h, p, st) : launch_axis_reg<L, true, false, false, true, true>(h, p, st);
         return p.dir < 0 ? launch_axis_reg<L, false, false, false, true>(h, p, st) : launch_axis_reg<L, true, false, false, true>(h, p, st);
+    }
+    if (dense && L >= 2048) {   // the free-space passes and plain transforms of the large configurations
+        if (p.roundtrip) {
+            if (cols) return p.dir < 0 ? launch_axis_reg<L, false, true, true, false, true>(h, p, st) : launch_axis_reg<L, true, true, true, false, true>(h, p, st);
+        } else if (!cols) {
+            return p.dir < 0 ? launch_axis_reg<L, false, false, false, false, true>(h, p, st) : launch_axis_reg<L, true, false, false, false, true>(h, p, st);
+        } else {
+            return p.dir < 0 ? launch_axis_reg<L, false, true, false, false, true>(h, p, st) : launch_axis_reg<L, true, true, false, false, true>(h, p, st);
+        }
     }
     if (p.roundtrip) {
         if (p.dir < 0) return cols ? launch_axis_reg<L, false, true, true>(h, p, st) : launch_axis_reg<L, false, false, true>(h, p, st);
@@ -1276,7 +1317,8 @@ int dispatch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
 int try_tuned_axis_pass(Handle* h, const AxisPass& p, cudaStream_t st) {
     static const bool disabled = getenv("PB_DISABLE_TUNED") != nullptr || getenv("PB_DISABLE_TUNED_AXIS") != nullptr;
     if (disabled) return PB_ERR_UNSUPPORTED;
-    if (p.dtype != PB_C64 || p.in_kind == PB_IN_AMP_OPD || p.out_kind != PB_OUT_COMPLEX) return PB_ERR_UNSUPPORTED;
+    if (p.dtype != PB_C64 || p.in_kind == PB_IN_AMP_OPD) return PB_ERR_UNSUPPORTED;
+    if (p.out_kind != PB_OUT_COMPLEX && !p.roundtrip) return PB_ERR_UNSUPPORTED;   // |.|^2 stores: round-trip epilogue only
     if (p.pre_e2 || (p.post_e2 && !p.roundtrip) || p.post_mat) return PB_ERR_UNSUPPORTED;
     if (p.Llog != p.L || (p.Llog_out != 0 && p.Llog_out != p.L)) return PB_ERR_UNSUPPORTED;
     // any batch: a single line (the kernel spectrum of a CZT plan, built per wavelength) takes 23 us on the generic

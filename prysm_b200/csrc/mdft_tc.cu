@@ -236,14 +236,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
             mbar_wait(&full[s], ph);
             float4* st = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
             auto split = [&](float4* hi, float4* lo, int n4) {
-#pragma unroll 4
-                for (int i = ct; i < n4; i += 64) {
-                    // hi = the value as the tensor core will read it (fp32 -> TF32 is a truncation): left in place, not
-                    // rewritten; lo = rn_tf32(x - hi) captures that truncation exactly and is itself TF32-exact, so the
-                    // split is unbiased at no extra shared-memory traffic
-                    const float4 v = hi[i];
-                    lo[i] = make_float4(tf32_rn(v.x - tf32_trunc(v.x)), tf32_rn(v.y - tf32_trunc(v.y)),
-                                        tf32_rn(v.z - tf32_trunc(v.z)), tf32_rn(v.w - tf32_trunc(v.w)));
+                // hi = the value as the tensor core will read it (fp32 -> TF32 is a truncation): left in place, not
+                // rewritten; lo = rn_tf32(x - hi) captures that truncation exactly and is itself TF32-exact, so the
+                // split is unbiased at no extra shared-memory traffic.  All loads of a batch are issued before the first
+                // use: the conversion sits between the TMA landing and the MMA issue, its latency is on the critical path.
+                constexpr int BATCH = 8;     // tiles are multiples of 64 * BATCH float4
+                for (int i0 = ct; i0 < n4; i0 += 64 * BATCH) {
+                    float4 v[BATCH];
+#pragma unroll
+                    for (int j = 0; j < BATCH; ++j) v[j] = hi[i0 + 64 * j];
+#pragma unroll
+                    for (int j = 0; j < BATCH; ++j)
+                        lo[i0 + 64 * j] = make_float4(tf32_rn(v[j].x - tf32_trunc(v[j].x)), tf32_rn(v[j].y - tf32_trunc(v[j].y)),
+                                                      tf32_rn(v[j].z - tf32_trunc(v[j].z)), tf32_rn(v[j].w - tf32_trunc(v[j].w)));
                 }
             };
             split(st, st + A_TILE / 16, A_TILE / 16);

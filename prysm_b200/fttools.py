@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _ops
+from ._capi import OUT_INTENSITY, OUT_ACCUMULATE
 from ._capi import OP_N, OP_T, OP_H, OP_C  # noqa: F401
 from .conf import config
 
@@ -136,6 +137,9 @@ def _expi(turns):
     return np.exp(2j * np.pi * fr)
 
 
+_ENGINE_MAX_K = 4096     # longest Bluestein length the register-resident axis engine runs (csrc/fft_tuned.cu)
+
+
 class _CztAxis:
     """Per-axis Bluestein pieces (prysm/fttools.py:372-389), built in fp64 on the host."""
 
@@ -175,57 +179,91 @@ class CZT:
         dy, dfy = float(y[1] - y[0]), float(fy[1] - fy[0])
         cd = config.complex_dtype
         dev = _ops.device()
-        Kx, Ky = next_fast_len(Nx + Mx - 1), next_fast_len(Ny + My - 1)
-        # the chirps, phase ramps and kernel spectra are built on the device from ten scalars per axis
-        # (fp64 phases): constructing an executor per wavelength costs no host maths and no uploads
-        px = (Nx, Mx, Kx, float(fx[Mx // 2]) / dfx, dx * dfx, sign, float(x[Nx // 2]), float(fx[0]), dfx)
-        py = (Ny, My, Ky, float(fy[My // 2]) / dfy, dy * dfy, sign, float(y[Ny // 2]), float(fy[0]), dfy)
-        self._bx, self._postx, self._Hx, self._Hadjx = _ops.czt_plan(*px, cd, dev)
-        if py == px:   # square, centred geometry (every BASELINE config): one plan serves both axes
-            self._by, self._posty, self._Hy, self._Hadjy = self._bx, self._postx, self._Hx, self._Hadjx
-        else:
-            self._by, self._posty, self._Hy, self._Hadjy = _ops.czt_plan(*py, cd, dev)
-        self._Nx, self._Ny, self._Mx, self._My, self._Kx, self._Ky = Nx, Ny, Mx, My, Kx, Ky
-        x_first_cost = Ny * Kx * math.log2(Kx) + Mx * Ky * math.log2(Ky)
-        y_first_cost = Nx * Ky * math.log2(Ky) + My * Kx * math.log2(Kx)
+        # One Bluestein plan per axis -- or TWO half-length plans when N + M - 1 exceeds the longest transform of the
+        # register-resident engine (4096): sum_n a[n] exp(s 2 pi i x_n f_m) splits exactly into the sums over the two halves
+        # of the input, each a CZT of length N/2 on its own sub-grid (own centre coordinate), and N/2 + M - 1 <= 4096 keeps
+        # both on the fast kernels (C5's final focus 4096 -> 512: 2 x K = 4096 instead of K = 8192 on the generic kernel).
+        # The chirps, phase ramps and kernel spectra are built on the device from ten scalars per plan (fp64 phases):
+        # constructing an executor per wavelength costs no host maths and no uploads.
+        def plans(xv, fv, N, M):
+            d, df = float(xv[1] - xv[0]), float(fv[1] - fv[0])
+            K = next_fast_len(N + M - 1)
+            if K > _ENGINE_MAX_K and N % 2 == 0 and next_fast_len(N // 2 + M - 1) <= _ENGINE_MAX_K:
+                parts = [(0, N // 2), (N // 2, N // 2)]
+            else:
+                parts = [(0, N)]
+            out = []
+            for start, n in parts:
+                sub = xv[start:start + n]
+                out.append((start, (n, M, next_fast_len(n + M - 1), float(fv[M // 2]) / df, d * df, sign, float(sub[n // 2]), float(fv[0]), df)))
+            return out
+        px, py = plans(x, fx, Nx, Mx), plans(y, fy, Ny, My)
+        built = {}
+
+        def build(params):
+            if params not in built:      # square, centred geometry (every BASELINE config): one plan serves both axes
+                built[params] = _ops.czt_plan(*params, cd, dev)
+            return built[params]
+        # per axis: list of (input offset, n, K, b, post, H, Hadj)
+        self._ax = [(s, p[0], p[2]) + tuple(build(p)) for s, p in px]
+        self._ay = [(s, p[0], p[2]) + tuple(build(p)) for s, p in py]
+        self._Nx, self._Ny, self._Mx, self._My = Nx, Ny, Mx, My
+        Kx, Ky = self._ax[0][2], self._ay[0][2]
+        self._bx = self._ax[0][3]
+        x_first_cost = Ny * Kx * math.log2(Kx) * len(self._ax) + Mx * Ky * math.log2(Ky) * len(self._ay)
+        y_first_cost = Nx * Ky * math.log2(Ky) * len(self._ay) + My * Kx * math.log2(Kx) * len(self._ax)
         self._x_first = x_first_cost <= y_first_cost
+
+    def _forward_axis(self, o, axis, parts, M, scale):
+        # ONE fused call per part: chirp -> FFT_K -> kernel spectrum -> IFFT_K -> slice -> chirp*phase.
+        # (the row chirp by[y] of the reference's `out *= brow` commutes with the x pass: it is the y pass's pre_e)
+        acc = None
+        for start, n, K, b, post, H, _ in parts:
+            piece = o[:, start:start + n] if axis == 1 else o[start:start + n]
+            r = _ops.czt_axis(piece, K, axis, b, H, post, n - 1, M, scale)
+            acc = r if acc is None else _ops.binary('add', acc, r)
+        return acc
+
+    def _adjoint_axis(self, o, axis, parts, scale):
+        # conj(post) -> FFT_K -> conj(H) with the embedding offset folded in -> IFFT_K -> [:n] -> conj(chirp), per part
+        outs = [_ops.czt_axis(o, K, axis, post, Hadj, b, 0, n, scale, pre_conj=True, post_conj=True)
+                for _, n, K, b, post, _, Hadj in parts]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=axis)
 
     def __call__(self, ary):
         o = _prep(ary, self._bx.dtype)
         if tuple(o.shape) != (self._Ny, self._Nx):
             raise ValueError(f'array of shape {tuple(o.shape)} does not match the executor')
-        Kx, Ky = self._Kx, self._Ky
-        # per axis ONE fused call: chirp -> FFT_K -> kernel spectrum -> IFFT_K -> slice -> chirp*phase.
-        # (the row chirp by[y] of the reference's `out *= brow` commutes with the x pass: it is the y pass's pre_e)
-        def along_x(o, scale):
-            return _ops.czt_axis(o, Kx, 1, self._bx, self._Hx, self._postx, self._Nx - 1, self._Mx, scale)
-
-        def along_y(o, scale):
-            return _ops.czt_axis(o, Ky, 0, self._by, self._Hy, self._posty, self._Ny - 1, self._My, scale)
-
         if self._x_first:
-            return along_y(along_x(o, 1.0), self.norm)
-        return along_x(along_y(o, 1.0), self.norm)
+            return self._forward_axis(self._forward_axis(o, 1, self._ax, self._Mx, 1.0), 0, self._ay, self._My, self.norm)
+        return self._forward_axis(self._forward_axis(o, 0, self._ay, self._My, 1.0), 1, self._ax, self._Mx, self.norm)
+
+    def intensity(self, ary, weight=1.0, out=None):
+        """|self(ary)|^2, written to a new real array or, with `out`, accumulated as out += weight * |.|^2: the modulus
+        is formed in the store of the last axis pass, the complex focal field is never written (one wavelength of an
+        incoherent sum; prysm/propagation/wavefront.py:147-151 + prysm/polynomials/fitting.py:37)."""
+        o = _prep(ary, self._bx.dtype)
+        if tuple(o.shape) != (self._Ny, self._Nx):
+            raise ValueError(f'array of shape {tuple(o.shape)} does not match the executor')
+        first = (1, self._ax, self._Mx) if self._x_first else (0, self._ay, self._My)
+        last = (0, self._ay, self._My) if self._x_first else (1, self._ax, self._Mx)
+        if len(last[1]) != 1:      # split last axis: the two halves add as fields, so the modulus cannot be fused
+            return _ops.intensity(self(ary), weight=weight, out=out)
+        mid = self._forward_axis(o, first[0], first[1], first[2], 1.0)
+        _, n, K, b, post, H, _ = last[1][0]
+        kind = OUT_INTENSITY if out is None else OUT_ACCUMULATE
+        return _ops.czt_axis(mid, K, last[0], b, H, post, n - 1, last[2], self.norm, out_kind=kind, weight=weight, out=out)
 
     def adjoint(self, grad):
         o = _prep(grad, self._bx.dtype)
         if tuple(o.shape) != (self._My, self._Mx):
             raise ValueError(f'array of shape {tuple(o.shape)} does not match the executor')
-        Kx, Ky = self._Kx, self._Ky
-
-        # conj(post) -> FFT_K -> conj(H) with the embedding offset folded in -> IFFT_K -> [:N] -> conj(chirp)
-        def back_x(o, scale):
-            return _ops.czt_axis(o, Kx, 1, self._postx, self._Hadjx, self._bx, 0, self._Nx, scale, pre_conj=True, post_conj=True)
-
-        def back_y(o, scale):
-            return _ops.czt_axis(o, Ky, 0, self._posty, self._Hadjy, self._by, 0, self._Ny, scale, pre_conj=True, post_conj=True)
-
         if self._x_first:  # undo y then x
-            return back_x(back_y(o, 1.0), self.norm)
-        return back_y(back_x(o, 1.0), self.norm)
+            return self._adjoint_axis(self._adjoint_axis(o, 0, self._ay, 1.0), 1, self._ax, self.norm)
+        return self._adjoint_axis(self._adjoint_axis(o, 1, self._ax, 1.0), 0, self._ay, self.norm)
 
     def nbytes(self):
-        vs = {id(v): v for v in (self._bx, self._Hx, self._postx, self._Hadjx, self._by, self._Hy, self._posty, self._Hadjy)}
+        vs = {id(v): v for part in self._ax + self._ay for v in part[3:]}
         return sum(v.numel() * v.element_size() for v in vs.values())
 
 
