@@ -79,8 +79,9 @@ def make_pupils(count, seed0=20260923):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=20):
         self.index = index
+        self.interval_ms = interval_ms
         self.rows = []
         self.proc = None
 
@@ -90,7 +91,7 @@ class ClockSampler:
              'clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.index), '-lms', '20'],
+                                          '-i', str(self.index), '-lms', str(self.interval_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -514,14 +515,24 @@ def run_b200(args):
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'MEASURED_PEAKS.json hbm_gbs (measured)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
 
-    # ---- extras that run on every rank (they contain collectives / barriers)
+    # ---- extras: the single-GPU ones first (rank 0 at N = 1), then the ones every rank takes part in (collectives / barriers).
+    # No nvidia-smi sampling around them: NVML queries contend with kernel launches for the driver, and the launch-heavy
+    # C4 loop (~10 launches per wavelength) measured 17-40 % slower with a sampler process starting beside it; they are
+    # bursts of < 0.2 s that run at the maximum clock.
     extras = {}
     if not args.no_extras:
+        if world == 1:
+            for name, fn in (('fused_psf', lambda: measure_fused_psf(stack[:8], peak)),
+                             ('mdft_c3', lambda: measure_mdft_c3(peaks))):
+                try:
+                    extras[name] = fn()
+                except Exception as exc:  # an extra never takes the headline line down with it
+                    extras[name] = {'error': repr(exc)[:300]}
         for name, fn in (('c4_polychromatic', lambda: measure_c4(dev, world, rank, barrier, peak)),
                          ('c5_free_space', lambda: measure_c5(dev, world, barrier, peak))):
             try:
                 extras[name] = fn()
-            except Exception as exc:  # an extra never takes the headline line down with it
+            except Exception as exc:
                 extras[name] = {'error': repr(exc)[:300]}
                 barrier()
             torch.cuda.empty_cache()
@@ -572,13 +583,6 @@ def run_b200(args):
         if cpu is not None:
             line['cpu_baseline'] = cpu
         line.update(extras)
-        if world == 1 and not args.no_extras:
-            for name, fn in (('mdft_c3', lambda: measure_mdft_c3(peaks)),
-                             ('fused_psf', lambda: measure_fused_psf(stack[:8], peak))):
-                try:
-                    line[name] = fn()
-                except Exception as exc:
-                    line[name] = {'error': repr(exc)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
