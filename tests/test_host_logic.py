@@ -103,3 +103,54 @@ def test_widened_rows_host_checks_need_no_gpu():
     assert polynomials.fringe_to_nm(1) == (0, 0) and polynomials.fringe_to_nm(4) == (2, 0)
     assert polynomials.zernike_norm(4, 0) == pytest.approx(math.sqrt(5))
     assert propagation.MultiResolutionExecutor([1, 2], [3, 4], [5, 6], [7, 8]).__len__() == 2
+
+
+# ------------------------------------------------------------------------------------------
+# round-2 host logic: validation of caller-supplied outputs, the bounded handle cache
+# ------------------------------------------------------------------------------------------
+def test_check_out_rejects_what_the_kernel_would_misread():
+    """A user `out=` reaches the kernel as a raw pointer + pitch: wrong dtype / shape / device / stride must raise
+    instead of writing out of bounds.  Pure host logic: CPU tensors suffice."""
+    import torch
+    from prysm_b200 import _ops
+    ok = torch.empty((4, 6), dtype=torch.float32)
+    assert _ops._check_out(ok, (4, 6), torch.float32, ok.device) is ok
+    with pytest.raises(ValueError, match='dtype'):
+        _ops._check_out(torch.empty((4, 6), dtype=torch.float64), (4, 6), torch.float32, ok.device)
+    with pytest.raises(ValueError, match='shape'):
+        _ops._check_out(torch.empty((4, 5), dtype=torch.float32), (4, 6), torch.float32, ok.device)
+    with pytest.raises(ValueError, match='stride'):
+        _ops._check_out(torch.empty((6, 4), dtype=torch.float32).t(), (4, 6), torch.float32, ok.device)
+    with pytest.raises(ValueError, match='is on'):
+        _ops._check_out(ok, (4, 6), torch.float32, torch.device('meta'))
+    with pytest.raises(TypeError):
+        _ops._check_out(np.zeros((4, 6), dtype=np.float32), (4, 6), torch.float32, ok.device)
+
+
+def test_handle_cache_is_bounded_and_pins_graph_streams(monkeypatch):
+    """One engine handle per (device, stream), at most MAX_HANDLES_PER_DEVICE un-pinned ones per device, least recently
+    used first out; pinned handles (CUDA-graph capture streams) survive; release_handle closes on demand."""
+    from prysm_b200 import _capi
+    closed = []
+
+    class Fake:
+        def __init__(self, device):
+            self.device = device
+
+        def close(self):
+            closed.append(self)
+    monkeypatch.setattr(_capi, 'Handle', Fake)
+    monkeypatch.setattr(_capi, '_handles', {})
+    monkeypatch.setattr(_capi, '_pinned', set())
+    cap = _capi.MAX_HANDLES_PER_DEVICE
+    first = _capi.handle_for(0, 100)
+    _capi.pin_handle(0, 100)
+    hs = [_capi.handle_for(0, 200 + i) for i in range(cap)]
+    assert _capi.handle_for(0, 200) is hs[0]                      # a hit refreshes its recency
+    _capi.handle_for(0, 999)                                      # one too many un-pinned handles on device 0
+    assert closed == [hs[1]] and (0, 201) not in _capi._handles   # the least recently used un-pinned one went
+    assert _capi.handle_for(0, 100) is first and first not in closed
+    _capi.handle_for(1, 5)                                        # another device has its own budget
+    assert len(closed) == 1
+    _capi.release_handle(0, 100)
+    assert first in closed and (0, 100) not in _capi._handles and (0, 100) not in _capi._pinned
