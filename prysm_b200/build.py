@@ -35,6 +35,17 @@ def _digest():
     return hsh.hexdigest()
 
 
+def _header_digest():
+    hsh = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + ['../../include/prysm_b200.h']:
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p) and not f.endswith('.cu'):
+            hsh.update(f.encode())
+            hsh.update(open(p, 'rb').read())
+    hsh.update(' '.join(FLAGS).encode())
+    return hsh.hexdigest()
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, 'build.stamp')
@@ -43,9 +54,15 @@ def build(force=False, verbose=False):
         return LIB
     objdir = os.path.join(LIBDIR, 'obj')
     os.makedirs(objdir, exist_ok=True)
+    hdig = _header_digest()
 
     def compile_one(src):
+        # incremental: an object is rebuilt when its source, any header or the flags changed
         obj = os.path.join(objdir, src[:-3] + '.o')
+        ostamp = obj + '.stamp'
+        odig = hashlib.sha256(open(os.path.join(CSRC, src), 'rb').read() + hdig.encode()).hexdigest()
+        if not force and os.path.exists(obj) and os.path.exists(ostamp) and open(ostamp).read() == odig:
+            return obj
         cmd = [NVCC, *FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
@@ -55,6 +72,7 @@ def build(force=False, verbose=False):
             raise RuntimeError(f'nvcc failed on {src}:\n{r.stdout}\n{r.stderr}')
         if verbose and r.stderr:
             print(r.stderr)
+        open(ostamp, 'w').write(odig)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:

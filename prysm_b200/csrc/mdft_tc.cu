@@ -310,6 +310,233 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
+// =====================================================================================================
+// CTA-pair form (tcgen05 cta_group::2): two CTAs of a cluster compute one 256 x 256 tile.  CTA r owns rows
+// m0 + 128 r .. of A (its own A_hi / A_lo tiles and its own 128-lane accumulators) and loads HALF of the B tile
+// (rows n0 + 128 r ..); the pair's MMA (M = 256, N = 256, issued by the leader CTA only) reads A from each CTA's own
+// shared memory and the two halves of B from both.  Per CTA and K-block the tensor core reads 96 KB of operands instead
+// of 144 KB and TMA writes 48 KB instead of 80 KB: the single-CTA kernel is bound by exactly that shared-memory
+// traffic.  A stage is 64 KB (96), so the ring is three deep.  Arithmetic, accumulation order and drain
+// schedule are those of tc_gemm_kernel: the results are bit-identical.
+// Synchronisation across the pair: every CTA's TMA completes on its OWN full barrier; its converter warps form A_lo
+// and then arrive (release.cluster) on the LEADER's conv barrier (4 arrivals: 2 warps x 2 CTAs); the leader's MMA
+// thread waits there, issues, and commits with multicast to BOTH CTAs' empty / tmem_full barriers; the epilogue
+// warps of both CTAs arrive on the leader's tmem_empty barrier (16 arrivals).
+// =====================================================================================================
+constexpr int STAGES2 = 3;
+constexpr uint32_t B_HALF = (BN / 2) * BK * 4;                     // 16 KB
+constexpr uint32_t STAGE2_BYTES = 2 * A_TILE + 2 * B_HALF;         // 64 KB
+constexpr uint32_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {   // arrives on `bar` of BOTH CTAs once the issued MMAs are done
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmBhi,
+                    const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* full = bars;                 // [STAGES2]  own TMA -> own converters
+    uint64_t* empty = bars + STAGES2;      // [STAGES2]  pair MMA -> own TMA producer (multicast commit)
+    uint64_t* conv = bars + 2 * STAGES2;   // [STAGES2]  converters of both CTAs -> MMA (the leader's copy is used)
+    uint64_t* tmem_full = bars + 3 * STAGES2;       // pair MMA -> own epilogue (multicast commit)
+    uint64_t* tmem_empty = bars + 3 * STAGES2 + 1;  // epilogues of both CTAs -> MMA (the leader's copy is used)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES2 + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int m0 = blockIdx.x * BM;                 // this CTA's 128 rows (blockIdx.x = 2 * pair + rank)
+    const int n0 = blockIdx.y * BN;                 // the pair's 256 columns
+    const int nb0 = n0 + (int)rank * (BN / 2);      // the half of the B tile this CTA loads
+    const int kb0 = blockIdx.z * p.kblocks;
+    const int CHUNK = p.chunk;
+    const int nchunks = (p.kblocks + CHUNK - 1) / CHUNK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 4); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 16);  // one arrival per epilogue warp of the pair
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {  // the same warp of both CTAs: all 512 columns in each, [0,256) main, [256,512) correction
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();    // barriers of both CTAs are initialised before anything arrives on them from the other side
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (kb / STAGES2) & 1;
+                mbar_wait_cluster(&empty[s], ph ^ 1);
+                unsigned char* st = smem + s * STAGE2_BYTES;
+                mbar_expect_tx(&full[s], A_TILE + 2 * B_HALF);
+                const int kc = (kb0 + kb) * BK;
+                tma_load_2d(st, &tmAhi, kc, m0, &full[s]);                       // fp32 A: read as TF32 it IS the hi part
+                tma_load_2d(st + 2 * A_TILE, &tmBhi, kc, nb0, &full[s]);
+                tma_load_2d(st + 2 * A_TILE + B_HALF, &tmBlo, kc, nb0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader CTA only) =====
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 256 (128 per CTA)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            const uint32_t d_main = tmem_base, d_corr = tmem_base + 256;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (kb / STAGES2) & 1;
+                const int c = kb / CHUNK, kin = kb - c * CHUNK;
+                if (kin == 0 && c > 0) {  // both epilogues must have drained the previous chunk
+                    mbar_wait_cluster(tmem_empty, (c - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait_cluster(&conv[s], ph);   // both CTAs: TMA landed AND the converter warps wrote the lo tiles
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + s * STAGE2_BYTES);
+                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE);
+                const uint64_t b_hi = make_desc(sa + 2 * A_TILE), b_lo = make_desc(sa + 2 * A_TILE + B_HALF);
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 8 tf32 = 32 B along K inside the swizzle row
+                    umma_tf32_pair(d_main, a_hi + adv, b_hi + adv, idesc, (kin | ks) != 0);
+                    umma_tf32_pair(d_corr, a_hi + adv, b_lo + adv, idesc, (kb | ks) != 0);
+                    umma_tf32_pair(d_corr, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+                umma_commit_pair(&empty[s]);   // frees the stage in both CTAs once these MMAs have read it
+                if (kin == CHUNK - 1 || kb == p.kblocks - 1) umma_commit_pair(tmem_full);  // chunk complete, both CTAs
+            }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===== converters (both CTAs): lo = rn_tf32(x - tf32(x)) of the own A tile, in the swizzled layout =====
+        const int ct = threadIdx.x - 2 * 32;
+        const uint32_t conv0 = mapa_u32(smem_u32(conv), 0);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+            const int s = kb % STAGES2;
+            const uint32_t ph = (kb / STAGES2) & 1;
+            mbar_wait(&full[s], ph);
+            float4* hi = reinterpret_cast<float4*>(smem + s * STAGE2_BYTES);
+            float4* lo = hi + A_TILE / 16;
+            constexpr int BATCH = 8;     // A_TILE / 16 = 1024 float4 = 2 x (64 threads x 8)
+            for (int i0 = ct; i0 < (int)(A_TILE / 16); i0 += 64 * BATCH) {
+                float4 v[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) v[j] = hi[i0 + 64 * j];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j)
+                    lo[i0 + 64 * j] = make_float4(tf32_rn(v[j].x - tf32_trunc(v[j].x)), tf32_rn(v[j].y - tf32_trunc(v[j].y)),
+                                                  tf32_rn(v[j].z - tf32_trunc(v[j].z)), tf32_rn(v[j].w - tf32_trunc(v[j].w)));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(conv0 + s * 8);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs, each its own 128 accumulator lanes): drain chunks, then transposed stores =====
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;    // which 128 of the 256 tile columns
+        const int m = m0 + q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+        const uint32_t tmem_empty0 = mapa_u32(smem_u32(tmem_empty), 0);
+        float tot[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) tot[i] = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait_cluster(tmem_full, c & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+                uint32_t a[16];
+                tmem_ld16(taddr + c0, a);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i) tot[c0 + i] += __uint_as_float(a[i]);
+            }
+            if (c + 1 < nchunks) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tmem_empty0);
+            }
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+            uint32_t b[16];
+            tmem_ld16(taddr + 256 + c0, b);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tot[c0 + i] += __uint_as_float(b[i]);
+        }
+        const int nb = n0 + half * 128;
+        if (p.mode == 0) {
+            float2* __restrict__ hi = reinterpret_cast<float2*>(p.out_hi);
+#pragma unroll
+            for (int c = 0; c < 128; c += 2) {
+                const long long o = (long long)((nb + c) >> 1) * p.ldo + m;
+                hi[o] = make_float2(tot[c], tot[c + 1]);
+            }
+        } else {
+            float* __restrict__ ws = p.out_hi + (long long)blockIdx.z * p.split_stride;
+#pragma unroll
+            for (int c = 0; c < 128; ++c) ws[(long long)(nb + c) * p.ldo + m] = tot[c];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();   // the leader's MMAs read the peer's shared memory: neither CTA leaves before both are done
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
 // complex basis E (m,n) -> real expansion (2m, 2n), hi and lo
 __global__ void expand_basis_kernel(const float2* __restrict__ E, int m, int n, float* __restrict__ hi, float* __restrict__ lo) {
     const long long tot = (long long)m * n;
@@ -378,6 +605,27 @@ int launch_gemm(Handle* h, const float* A, const float* Bhi, const float* Blo, i
     return PB_OK;
 }
 
+// the CTA-pair form: M a multiple of 256 (pairs of 128-row tiles along x)
+int launch_gemm_pair(Handle* h, const float* A, const float* Bhi, const float* Blo, int M, int N, long long K,
+                     int splits, const GemmParams& gp, cudaStream_t st) {
+    CUtensorMap mAhi, mBhi, mBlo;
+    PB_TRY(make_map(h, &mAhi, A, M, K, BM));
+    PB_TRY(make_map(h, &mBhi, Bhi, N, K, BN / 2));
+    PB_TRY(make_map(h, &mBlo, Blo, N, K, BN / 2));
+    if (attr_needed(h, reinterpret_cast<const void*>(tc_gemm_pair_kernel)))
+        PB_CUDA(h, cudaFuncSetAttribute(tc_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(M / BM, N / BN, splits);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM2_BYTES;
+    cfg.stream = st;
+    cfg.attrs = nullptr;     // the cluster shape is compiled in (__cluster_dims__)
+    cfg.numAttrs = 0;
+    PB_CUDA(h, cudaLaunchKernelEx(&cfg, tc_gemm_pair_kernel, mAhi, mBhi, mBlo, gp));
+    PB_LAUNCH_CHECK(h);
+    return PB_OK;
+}
+
 int pick_splits(int ny) {
     // stage 2 has only (Mx/128)*(2My/256) tiles; split its long contraction (2*Ny) to fill the GPU
     const long long kblocks = 2LL * ny / BK;
@@ -432,15 +680,21 @@ extern "C" int pb_mdft_tc_apply(pb_handle_t hh, const void* ExB_hi, const void* 
     // 16 -> 2e-6, 8 -> 1.5e-6, 4 -> 1.2e-6, 2 -> 9e-7 on random data; the drains hide behind the L2-bound mainloop)
     static const int chunk = [] { const char* e = getenv("PB_MDFT_CHUNK"); return e ? std::max(1, atoi(e)) : 2; }();
     static const int conv_b = [] { const char* e = getenv("PB_MDFT_CONV_B"); return e ? atoi(e) : 0; }();
+    // PB_MDFT_PAIR=1 selects the CTA-pair kernel (cta_group::2) wherever the tile rows come in pairs.  Opt-in: bit-identical
+    // results, but the drain handshake crosses the pair and costs more than the halved operand traffic saves at the
+    // drain interval the 1e-6 budget needs (487 us against 393 us at C3 with chunk = 2; 365 us with no drains at all)
+    static const int pair = [] { const char* e = getenv("PB_MDFT_PAIR"); return e ? atoi(e) : 0; }();
     float* t1 = reinterpret_cast<float*>(work);
     float* ws = t1 + 2LL * ny * mx;
     {   // stage 1: T1^T(mx, ny) = (a @ Ex^T)^T : M = ny rows of a, N = 2*mx expanded basis rows, K = 2*nx
         GemmParams gp{(int)(2LL * nx / BK), chunk, 0, conv_b, t1, nullptr, (long long)ny, 0};
-        PB_TRY(launch_gemm(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
+        if (pair && ny % (2 * BM) == 0) PB_TRY(launch_gemm_pair(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
+        else PB_TRY(launch_gemm(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
     }
     {   // stage 2: out^T' = T1^T' @ Ey'^T : M = mx, N = 2*my, K = 2*ny, split-K partials transposed into ws[s][2my][mx]
         GemmParams gp{(int)(2LL * ny / BK / splits), chunk, 1, conv_b, ws, nullptr, (long long)mx, 2LL * my * mx};
-        PB_TRY(launch_gemm(h, t1, (const float*)EyB_hi, (const float*)EyB_lo, mx, 2 * my, 2LL * ny, splits, gp, st));
+        if (pair && mx % (2 * BM) == 0) PB_TRY(launch_gemm_pair(h, t1, (const float*)EyB_hi, (const float*)EyB_lo, mx, 2 * my, 2LL * ny, splits, gp, st));
+        else PB_TRY(launch_gemm(h, t1, (const float*)EyB_hi, (const float*)EyB_lo, mx, 2 * my, 2LL * ny, splits, gp, st));
     }
     {
         const long long tot = (long long)my * mx;

@@ -1,5 +1,5 @@
 """GPU: tcgen05 MDFT vs the CUDA-core GEMM and the fp64 oracle; timing at the C3 size."""
-import os, sys, time
+import os, sys, time, hashlib
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
@@ -20,6 +20,7 @@ for (N, M) in ((256, 128), (512, 256), (1024, 128)):
     assert tc._tc is not None
     simt = F.MDFT(x, x, f, f, -1, 0.5, use_tensor_cores=False)
     o_tc = tc(a).cpu().numpy(); o_simt = simt(a).cpu().numpy()
+    print('  sha1', hashlib.sha1(o_tc.tobytes()).hexdigest()[:12], 'PB_MDFT_PAIR =', os.environ.get('PB_MDFT_PAIR', 'default'))
     print(f'N={N} M={M}: tc vs fp64 {rel(o_tc, ref):.2e}   simt vs fp64 {rel(o_simt, ref):.2e}   tc vs simt {rel(o_tc, o_simt):.2e}', flush=True)
 
 if '--big' in sys.argv:
@@ -32,6 +33,7 @@ if '--big' in sys.argv:
     out = ex(d); torch.cuda.synchronize()
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'full_c3.npz'))
     o = out.cpu().numpy(); amax = float(g['field_absmax'])
+    print('  sha1', hashlib.sha1(o.tobytes()).hexdigest()[:12])
     print('C3 tc vs reference fp64 (strided samples):', float(np.abs(o[::16, ::16] - g['field_stride']).max() / amax))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3): ex(d)
