@@ -17,9 +17,10 @@
 //     produced) has to be L2-resident;
 //   * the pipeline has no fill / drain bubble: every CTA starts in column mode (row workers help with field 0) and
 //     every CTA ends in row mode (column workers join the row workers when the tiles run out).
-// Cross-SM visibility: column warps fence (gpu scope) and add to cols_done a good part of a tile time AFTER the stores
-// they signal (the fence then finds the stores drained); the row group's requesting thread load-acquires the counter and
-// issues fence.proxy.async before the tensor-TMA gather of the row.
+// Cross-SM visibility: one thread per column group fences (gpu scope, cumulative over the group's barriers) and adds to
+// cols_done a good part of a tile time AFTER the stores it signals (the fence then finds the stores drained); the row
+// group's requesting thread load-acquires the counter and issues fence.proxy.async (all spaces, once per field) before
+// the tensor-TMA gathers of that field's rows.
 #include "fft_engine.cuh"
 
 namespace pb {
@@ -144,9 +145,17 @@ __device__ __forceinline__ void fused_col_group(const CUtensorMap& in_map, const
             }
         }
         fft_two_stages_u<L, INV, HALF>(v, t, S, plan + G4::TW1, plan + G4::TW2, u, sync);
-        if (have_pref) { ctl[3] = pref; have_pref = false; }
-        if (pending >= 0 && lane == 0) {   // the previous tile's stores left this warp three barriers ago
-            __threadfence();
+        if (have_pref) {
+            ctl[3] = pref;
+            have_pref = false;
+            if ((p.hints & 2) && pref >= 0) {   // pull the tile after next from HBM into L2 now: its gather will be an L2 hit
+                const int fb2 = pref / G2::TILES, tile2 = pref - fb2 * G2::TILES;
+#pragma unroll
+                for (int b = 0; b < G2::NBOX_IN; ++b) tma_prefetch_3d(&in_map, tile2 * 4, b * G2::BOXR, fb2);
+            }
+        }
+        if (pending >= 0 && lt == 0) {   // the previous tile's stores of ALL warps of the group are three group barriers old:
+            __threadfence();             // one cumulative gpu-scope fence by one thread publishes them
             atomicAdd(p.sync + 2 + pending, 1);
         }
         fft_last_stage_load<L, INV>(v, t, S);
@@ -174,8 +183,8 @@ __device__ __forceinline__ void fused_col_group(const CUtensorMap& in_map, const
             }
         pending = fb;
     }
-    __syncwarp();
-    if (pending >= 0 && lane == 0) {
+    gsync();   // every warp of the group has left the loop: its last tile's stores are ordered before the barrier
+    if (pending >= 0 && lt == 0) {
         __threadfence();
         atomicAdd(p.sync + 2 + pending, 1);
     }
@@ -203,8 +212,11 @@ __device__ __forceinline__ void fused_row_group(const CUtensorMap& tmp_map, cons
     auto request_row = [&](int R) {   // one thread: gather intermediate row R = (field, plane, j) into `inb`
         const int fb = R / (2 * L), rf = R - fb * (2 * L);
         const int ph = rf / L, j = rf - ph * L;
-        if (fb > ready_f) { spin_until(p.sync + 2 + fb, G2::TILES * GF::WARPS); ready_f = fb; }
-        fence_proxy_async_all();   // the row buffer's generic reads and the column workers' (acquired) stores before the async gather
+        // generic -> async proxy: the row buffer's reads always; the column workers' (acquired) global stores once per field --
+        // the all-space fence also waits for this thread's own output stores in flight, which is what made every group
+        // barrier after it the kernel's top stall when it was issued per row
+        if (fb > ready_f) { spin_until(p.sync + 2 + fb, G2::TILES * 2); ready_f = fb; fence_proxy_async_all(); }
+        else fence_proxy_async();
         const int grow = ((fb % p.ring) * 2 + ph) * (L / 4) + (j >> 2);
         mbar_expect_tx(bar, ROW_BYTES);
 #pragma unroll
@@ -373,7 +385,9 @@ int launch_fused(Handle* h, const void* in, long long in_ld, long long in_bs, in
     p.sync = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) + tmp_bytes);
     PB_TRY(get_col4_plan<L>(h, &p.plan));
     p.out = out; p.out_ld = out_ld; p.out_bs = out_bs; p.out_kind = out_kind; p.scale = scale; p.weight = weight;
-    p.batch = batch; p.ring = ring; p.ncol = ncol; p.help_tiles = G2::TILES; p.hints = hints & 1;
+    p.batch = batch; p.ring = ring; p.ncol = ncol; p.help_tiles = G2::TILES;
+    static const int prefetch = env_int("PB_FUSED_PREFETCH", 0);
+    p.hints = (hints & 1) | (prefetch ? 2 : 0);
     // (descriptors are copied out at once: the handle's cache may be flushed by the next lookup)
     const CUtensorMap* map = nullptr;
     CUtensorMap in_m, tmp_m;

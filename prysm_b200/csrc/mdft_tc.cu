@@ -38,8 +38,16 @@
 namespace pb {
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32;           // BK fp32 = 128 B = one swizzle row
-constexpr int STAGES = 2;
+// K extent of a pipeline stage, in fp32 = one swizzle row: 32 (128-byte swizzle, 96 KB stages, a ring of 2) or 16
+// (64-byte swizzle, 48 KB stages, a ring of 4).  The MMA of one 32-deep stage takes ~0.84 us, less than the L2 -> shared
+// latency of the next stage's 80 KB plus the lo-split behind it, and with two stages only one load is ever in flight:
+// the tensor pipe sat at 66 % (profiles/r02_ncu_mdft_summary.txt).  Four half-size stages keep three loads in flight.
+#ifndef PB_MDFT_BK
+#define PB_MDFT_BK 16
+#endif
+constexpr int BM = 128, BN = 256, BK = PB_MDFT_BK;
+static_assert(BK == 16 || BK == 32, "BK is one 64- or 128-byte swizzle row of fp32");
+constexpr int STAGES = BK == 32 ? 2 : 4;
 constexpr int NTHREADS = 384;   // warp 0 TMA, 1 MMA, 2-3 TMEM alloc + TF32 lo-split converters, 4-11 epilogue
 constexpr uint32_t A_TILE = BM * BK * 4;             // 16 KB
 constexpr uint32_t B_TILE = BN * BK * 4;             // 32 KB
@@ -73,14 +81,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
-// K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart
+// K-major, swizzled: rows of BK fp32 (128 or 64 B), 8-row groups 8 rows apart
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address
     d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row groups
+    d |= (uint64_t)((8 * BK * 4) >> 4) << 32;      // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;       // SWIZZLE_128B / SWIZZLE_64B
     return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -118,6 +126,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 struct GemmParams {
@@ -311,6 +325,235 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
 }
 
 // =====================================================================================================
+// Stream-K form of tc_gemm_kernel for grids that do not fill the GPU (stage 1 at C3 is 128 tiles on 148 SMs).
+// The work of a launch -- tiles x K-blocks, in units of one drain chunk -- is cut into gridDim.x equal contiguous
+// ranges, one per CTA (one CTA per SM).  A range covers the tail of one tile, possibly whole tiles, and the head of
+// another: the CTA walks its SEGMENTS (tile, K-block range) through the same TMA / converter / MMA / epilogue pipelines
+// as the classic kernel (ring stage and chunk phase counters simply run on across segments).  The segment that STARTS a
+// tile's K range owns the tile's output; it is its CTA's last segment.  Every segment that starts inside a tile is its
+// CTA's FIRST: it writes its partial tile to the CTA's slot of the workspace and publishes it (gpu-scope fence +
+// counter) before the CTA goes on, so a partial is never published after a wait.  The owner adds the partials of CTAs
+// g+1, g+2, ... in that fixed order (deterministic) and stores as the classic kernel does; by the time it gets there
+// they have long been published.  (Owning by the LAST piece instead chains every CTA behind its predecessor: 4.8 ms.)
+// =====================================================================================================
+struct SkParams {
+    GemmParams g;        // g.kblocks = K-blocks per TILE; g.chunk divides it; g.mode = 0
+    int ntn;             // tiles along N
+    int ntiles;          // tiles of the launch
+    float* part;         // [gridDim.x][256][128] partial tiles, column-major inside the tile
+    int* flags;          // [gridDim.x] epilogue warps of CTA g that have published its partial (zeroed before the launch)
+};
+
+struct SkSeg { int tile, kb0, kb1, m0, n0; };
+// segment of the CTA's range [u0, u1) that starts at unit u
+__device__ __forceinline__ SkSeg sk_segment(int u, int u1, int upt, int chunk, int ntn) {
+    SkSeg s;
+    s.tile = u / upt;
+    const int ub = u - s.tile * upt;
+    const int ue = min(upt, ub + (u1 - u));
+    s.kb0 = ub * chunk; s.kb1 = ue * chunk;
+    s.m0 = (s.tile / ntn) * BM; s.n0 = (s.tile % ntn) * BN;
+    return s;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmBhi,
+                  const __grid_constant__ CUtensorMap tmBlo, const SkParams sp) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;              // [STAGES]  TMA -> converters
+    uint64_t* empty = bars + STAGES;    // [STAGES]  MMA -> TMA
+    uint64_t* conv = bars + 2 * STAGES; // [STAGES]  converters -> MMA
+    uint64_t* tmem_full = bars + 3 * STAGES;       // MMA -> epilogue: a chunk is complete in TMEM
+    uint64_t* tmem_empty = bars + 3 * STAGES + 1;  // epilogue -> MMA: the accumulators were read
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
+
+    const GemmParams& p = sp.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int CHUNK = p.chunk;
+    const int upt = p.kblocks / CHUNK;                         // units (chunks) per tile
+    const long long U = (long long)sp.ntiles * upt;
+    const int G = gridDim.x, g = blockIdx.x;
+    const int u0 = (int)(U * g / G), u1 = (int)(U * (g + 1) / G);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 64); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 8);  // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            int i = 0;   // K-blocks of this CTA so far: ring stage and phase run on across segments
+            for (int u = u0; u < u1;) {
+                const SkSeg sg = sk_segment(u, u1, upt, CHUNK, sp.ntn);
+                for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++i) {
+                    const int s = i % STAGES;
+                    const uint32_t ph = (i / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    unsigned char* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full[s], A_TILE + 2 * B_TILE);
+                    const int kc = kb * BK;
+                    tma_load_2d(st, &tmAhi, kc, sg.m0, &full[s]);
+                    tma_load_2d(st + 2 * A_TILE, &tmBhi, kc, sg.n0, &full[s]);
+                    tma_load_2d(st + 2 * A_TILE + B_TILE, &tmBlo, kc, sg.n0, &full[s]);
+                }
+                u += (sg.kb1 - sg.kb0) / CHUNK;
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t d_main = tmem_base, d_corr = tmem_base + 256;
+            int i = 0, c = 0;   // K-blocks and chunks of this CTA so far
+            for (int u = u0; u < u1;) {
+                const SkSeg sg = sk_segment(u, u1, upt, CHUNK, sp.ntn);
+                for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++i) {
+                    const int s = i % STAGES;
+                    const uint32_t ph = (i / STAGES) & 1;
+                    const int kin = kb % CHUNK;          // segments start on chunk boundaries
+                    if (kin == 0 && c > 0) {  // the epilogue must have read the previous chunk (and, at a segment end, the correction accumulator)
+                        mbar_wait(tmem_empty, (c - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    mbar_wait(&conv[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE);
+                    const uint64_t b_hi = make_desc(sa + 2 * A_TILE), b_lo = make_desc(sa + 2 * A_TILE + B_TILE);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 32 >> 4);
+                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (kin | ks) != 0);
+                        umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, ((kb - sg.kb0) | ks) != 0);
+                        umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kin == CHUNK - 1) { umma_commit(tmem_full); ++c; }
+                }
+                u += (sg.kb1 - sg.kb0) / CHUNK;
+            }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===== converters: lo part of the A tile, see tc_gemm_kernel =====
+        const int ct = threadIdx.x - 2 * 32;
+        const int nkb = (u1 - u0) * CHUNK;
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (i / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+            float4* lo = hi + A_TILE / 16;
+            constexpr int BATCH = 8;
+            for (int i0 = ct; i0 < (int)(A_TILE / 16); i0 += 64 * BATCH) {
+                float4 v[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) v[j] = hi[i0 + 64 * j];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j)
+                    lo[i0 + 64 * j] = make_float4(tf32_rn(v[j].x - tf32_trunc(v[j].x)), tf32_rn(v[j].y - tf32_trunc(v[j].y)),
+                                                  tf32_rn(v[j].z - tf32_trunc(v[j].z)), tf32_rn(v[j].w - tf32_trunc(v[j].w)));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&conv[s]);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: per segment drain its chunks; then publish a partial tile or (tile owner) gather and store =====
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;    // which 128 of the 256 tile columns
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+        const int total_chunks = u1 - u0;
+        const long long slot = (long long)(half * 128) * BM + q * 32 + lane;   // this thread's first element of a partial tile
+        int c = 0;
+        for (int u = u0; u < u1;) {
+            const SkSeg sg = sk_segment(u, u1, upt, CHUNK, sp.ntn);
+            const int nseg = (sg.kb1 - sg.kb0) / CHUNK;
+            float tot[128];
+#pragma unroll
+            for (int i = 0; i < 128; ++i) tot[i] = 0.f;
+            for (int cs = 0; cs < nseg; ++cs) {
+                mbar_wait(tmem_full, c & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 16) {
+                    uint32_t a[16];
+                    tmem_ld16(taddr + c0, a);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) tot[c0 + i] += __uint_as_float(a[i]);
+                }
+                if (cs == nseg - 1) {   // the segment's MMAs are complete: fold its correction accumulator in
+#pragma unroll
+                    for (int c0 = 0; c0 < 128; c0 += 16) {
+                        uint32_t b[16];
+                        tmem_ld16(taddr + 256 + c0, b);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) tot[c0 + i] += __uint_as_float(b[i]);
+                    }
+                }
+                ++c;
+                if (c < total_chunks) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                }
+            }
+            if (sg.kb0 > 0) {
+                // a tail or middle piece of its tile: always the FIRST segment of this CTA, so it is published early and
+                // never after a wait -- the tile's owner (below) finds it ready when it gets there
+                float* __restrict__ dst = sp.part + (long long)g * (BM * BN) + slot;
+#pragma unroll
+                for (int cc = 0; cc < 128; ++cc) __stcg(dst + (long long)cc * BM, tot[cc]);
+                __syncwarp();
+                if (lane == 0) { __threadfence(); atomicAdd(sp.flags + g, 1); }
+            } else {
+                if (sg.kb1 < p.kblocks) {
+                    // the head of a tile whose K range continues in CTAs g+1, g+2, ...: this CTA owns the tile (it is its LAST
+                    // segment) and adds their partials in that fixed order
+                    const long long tile_u1 = (long long)(sg.tile + 1) * upt;
+                    for (int gp = g + 1; gp < G; ++gp) {
+                        if (lane == 0) { while (ld_acquire_gpu(sp.flags + gp) < 8) __nanosleep(64); }
+                        __syncwarp();
+                        const float* __restrict__ src = sp.part + (long long)gp * (BM * BN) + slot;
+#pragma unroll
+                        for (int cc = 0; cc < 128; ++cc) tot[cc] += __ldcg(src + (long long)cc * BM);
+                        if (U * (gp + 1) / G >= tile_u1) break;   // that piece reached the tile's last K-block
+                    }
+                }
+                const int m = sg.m0 + q * 32 + lane;
+                const int nb = sg.n0 + half * 128;
+                float2* __restrict__ hi = reinterpret_cast<float2*>(p.out_hi);
+#pragma unroll
+                for (int cc = 0; cc < 128; cc += 2) {
+                    const long long o = (long long)((nb + cc) >> 1) * p.ldo + m;
+                    hi[o] = make_float2(tot[cc], tot[cc + 1]);
+                }
+            }
+            u += nseg;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// =====================================================================================================
 // CTA-pair form (tcgen05 cta_group::2): two CTAs of a cluster compute one 256 x 256 tile.  CTA r owns rows
 // m0 + 128 r .. of A (its own A_hi / A_lo tiles and its own 128-lane accumulators) and loads HALF of the B tile
 // (rows n0 + 128 r ..); the pair's MMA (M = 256, N = 256, issued by the leader CTA only) reads A from each CTA's own
@@ -323,7 +566,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
 // thread waits there, issues, and commits with multicast to BOTH CTAs' empty / tmem_full barriers; the epilogue
 // warps of both CTAs arrive on the leader's tmem_empty barrier (16 arrivals).
 // =====================================================================================================
-constexpr int STAGES2 = 3;
+constexpr int STAGES2 = BK == 32 ? 3 : 6;
 constexpr uint32_t B_HALF = (BN / 2) * BK * 4;                     // 16 KB
 constexpr uint32_t STAGE2_BYTES = 2 * A_TILE + 2 * B_HALF;         // 64 KB
 constexpr uint32_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -584,7 +827,7 @@ int make_map(Handle* h, CUtensorMap* map, const void* base, long long rows, long
     const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, PB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return PB_OK;
@@ -601,6 +844,31 @@ int launch_gemm(Handle* h, const float* A, const float* Bhi, const float* Blo, i
         PB_CUDA(h, cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     dim3 grid(M / BM, N / BN, splits);
     tc_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mAhi, mBhi, mBlo, gp);
+    PB_LAUNCH_CHECK(h);
+    return PB_OK;
+}
+
+constexpr int SK_MAX_CTAS = 160;
+constexpr long long SK_WORK_BYTES = (long long)SK_MAX_CTAS * BM * BN * 4 + 4096;   // partial tiles + flags
+
+// stream-K form (mode 0 only): `work` = SK_WORK_BYTES of scratch
+int launch_gemm_sk(Handle* h, const float* A, const float* Bhi, const float* Blo, int M, int N, long long K,
+                   const GemmParams& gp, void* work, cudaStream_t st) {
+    CUtensorMap mAhi, mBhi, mBlo;
+    PB_TRY(make_map(h, &mAhi, A, M, K, BM));
+    PB_TRY(make_map(h, &mBhi, Bhi, N, K, BN));
+    PB_TRY(make_map(h, &mBlo, Blo, N, K, BN));
+    if (attr_needed(h, reinterpret_cast<const void*>(tc_gemm_sk_kernel)))
+        PB_CUDA(h, cudaFuncSetAttribute(tc_gemm_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SkParams sp;
+    sp.g = gp;
+    sp.ntn = N / BN;
+    sp.ntiles = (M / BM) * (N / BN);
+    sp.part = reinterpret_cast<float*>(work);
+    sp.flags = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + (long long)SK_MAX_CTAS * BM * BN * 4);
+    const int grid = std::min(h->sm_count, SK_MAX_CTAS);
+    PB_CUDA(h, cudaMemsetAsync(sp.flags, 0, SK_MAX_CTAS * sizeof(int), st));
+    tc_gemm_sk_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mAhi, mBhi, mBlo, sp);
     PB_LAUNCH_CHECK(h);
     return PB_OK;
 }
@@ -662,7 +930,7 @@ extern "C" long long pb_mdft_tc_work_bytes(int my, int ny, int mx, int nx) {
     (void)nx;
     const long long t1 = 2LL * ny * mx * 4;                   // T1^T (complex mx x ny)
     const long long ws = (long long)pick_splits(ny) * 2 * my * mx * 4;
-    return t1 + ws + 4096;
+    return t1 + ws + 4096 + SK_WORK_BYTES;
 }
 
 extern "C" int pb_mdft_tc_apply(pb_handle_t hh, const void* ExB_hi, const void* ExB_lo, const void* EyB_hi,
@@ -678,7 +946,7 @@ extern "C" int pb_mdft_tc_apply(pb_handle_t hh, const void* ExB_hi, const void* 
     const int splits = pick_splits(ny);
     // 2 K-blocks (8 main accumulation steps) per drain: < 1e-6 of the fp64 result at any K (measured:
     // 16 -> 2e-6, 8 -> 1.5e-6, 4 -> 1.2e-6, 2 -> 9e-7 on random data; the drains hide behind the L2-bound mainloop)
-    static const int chunk = [] { const char* e = getenv("PB_MDFT_CHUNK"); return e ? std::max(1, atoi(e)) : 2; }();
+    static const int chunk = [] { const char* e = getenv("PB_MDFT_CHUNK"); return (e ? std::max(1, atoi(e)) : 2) * (32 / BK); }();   // in K-blocks of BK
     static const int conv_b = [] { const char* e = getenv("PB_MDFT_CONV_B"); return e ? atoi(e) : 0; }();
     // PB_MDFT_PAIR=1 selects the CTA-pair kernel (cta_group::2) wherever the tile rows come in pairs.  Opt-in: bit-identical
     // results, but the drain handshake crosses the pair and costs more than the halved operand traffic saves at the
@@ -688,7 +956,16 @@ extern "C" int pb_mdft_tc_apply(pb_handle_t hh, const void* ExB_hi, const void* 
     float* ws = t1 + 2LL * ny * mx;
     {   // stage 1: T1^T(mx, ny) = (a @ Ex^T)^T : M = ny rows of a, N = 2*mx expanded basis rows, K = 2*nx
         GemmParams gp{(int)(2LL * nx / BK), chunk, 0, conv_b, t1, nullptr, (long long)ny, 0};
-        if (pair && ny % (2 * BM) == 0) PB_TRY(launch_gemm_pair(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
+        // stream-K when the tile grid does not fill the SMs evenly (C3: 128 tiles on 148 SMs); PB_MDFT_STREAMK=0 disables it
+        static const int streamk = [] { const char* e = getenv("PB_MDFT_STREAMK"); return e ? atoi(e) : 1; }();
+        const int tiles1 = (ny / BM) * (2 * mx / BN);
+        const bool sk_ok = streamk && !pair && gp.kblocks % chunk == 0 && tiles1 % h->sm_count != 0 &&
+                           (long long)tiles1 * (gp.kblocks / chunk) >= 4LL * h->sm_count;
+        if (sk_ok) {
+            char* skw = reinterpret_cast<char*>(ws + (long long)splits * 2 * my * mx);
+            skw += (16 - ((uintptr_t)skw & 15)) & 15;
+            PB_TRY(launch_gemm_sk(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, gp, skw, st));
+        } else if (pair && ny % (2 * BM) == 0) PB_TRY(launch_gemm_pair(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
         else PB_TRY(launch_gemm(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
     }
     {   // stage 2: out^T' = T1^T' @ Ey'^T : M = mx, N = 2*my, K = 2*ny, split-K partials transposed into ws[s][2my][mx]
