@@ -784,6 +784,56 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && (!COLS || TP 
         fft_last_stage_load<L, !INV>(w, t, S);
 #pragma unroll
         for (int g = 0; g < G::GI; ++g) dftR<G::R3, !INV>(w + g * G::R3);
+        if (COLS && p.out_kind != PB_OUT_COMPLEX && (p.batch_contiguous & 8) && hasB) {
+            // |.|^2 of a column pass onto a real plane, both columns of the thread as one aligned float2.  Three passes over
+            // the thread's 16 samples -- form the intensities, read ALL the previous plane values, then store -- because a
+            // read-modify-write per sample serialises: the compiler may not move sample i+1's load above sample i's store to
+            // the same array, and sixteen DRAM latencies in a row were the C4 column pass's top stall (long_scoreboard 8.2).
+            float* __restrict__ outr = reinterpret_cast<float*>(p.out);
+            const float s2 = scale * scale, wgt = (float)p.weight;
+            auto out_q = [&](int j) -> int {   // output sample of transform index j, or -1 when it is cropped away
+                if (DENSE) return j;
+                int q = j - p.crop_off + p.rot_out;
+                if (q < 0) q += L;
+                if (q >= L) q -= L;
+                return q < p.n_out ? q : -1;
+            };
+            float2 I[16];
+#pragma unroll
+            for (int g = 0; g < G::GI; ++g)
+#pragma unroll
+                for (int kk = 0; kk < G::R3; ++kk) {
+                    const int q = out_q(t + g * NT + 256 * kk);
+                    const P2 y = w[g * G::R3 + kk];
+                    float2 ya = make_float2(y.re.x, y.im.x), yb = make_float2(y.re.y, y.im.y);
+                    if (p.post_e2 && q >= 0) {
+                        const float2 m = reinterpret_cast<const float2*>(p.post_e2)[q];
+                        ya = cmul_s(ya, m, p.post_e2_conj); yb = cmul_s(yb, m, p.post_e2_conj);
+                    }
+                    I[g * G::R3 + kk] = make_float2(s2 * fmaf(ya.x, ya.x, ya.y * ya.y), s2 * fmaf(yb.x, yb.x, yb.y * yb.y));
+                }
+            if (p.out_kind == PB_OUT_ACCUMULATE) {
+#pragma unroll
+                for (int g = 0; g < G::GI; ++g)
+#pragma unroll
+                    for (int kk = 0; kk < G::R3; ++kk) {
+                        const int q = out_q(t + g * NT + 256 * kk);
+                        if (q < 0) continue;
+                        const float2 prev = *reinterpret_cast<const float2*>(outr + (long long)b0 * p.obs + (long long)q * p.oes);
+                        float2& v2 = I[g * G::R3 + kk];
+                        v2 = make_float2(fmaf(wgt, v2.x, prev.x), fmaf(wgt, v2.y, prev.y));
+                    }
+            }
+#pragma unroll
+            for (int g = 0; g < G::GI; ++g)
+#pragma unroll
+                for (int kk = 0; kk < G::R3; ++kk) {
+                    const int q = out_q(t + g * NT + 256 * kk);
+                    if (q < 0) continue;
+                    *reinterpret_cast<float2*>(outr + (long long)b0 * p.obs + (long long)q * p.oes) = I[g * G::R3 + kk];
+                }
+            return;
+        }
 #pragma unroll
         for (int g = 0; g < G::GI; ++g)
 #pragma unroll
@@ -813,12 +863,6 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && (!COLS || TP 
                     float* __restrict__ outr = reinterpret_cast<float*>(p.out);
                     const float s2 = scale * scale, wgt = (float)p.weight;
                     float ia = s2 * fmaf(ya.x, ya.x, ya.y * ya.y), ib = s2 * fmaf(yb.x, yb.x, yb.y * yb.y);
-                    if (COLS && (p.batch_contiguous & 8) && hasB) {   // the two columns' samples are one aligned float2
-                        float2* __restrict__ q2 = reinterpret_cast<float2*>(outr + o);
-                        if (p.out_kind == PB_OUT_ACCUMULATE) { const float2 prev = *q2; ia = fmaf(wgt, ia, prev.x); ib = fmaf(wgt, ib, prev.y); }
-                        *q2 = make_float2(ia, ib);
-                        continue;
-                    }
                     if (p.out_kind == PB_OUT_ACCUMULATE) {
                         if (hasA) ia = fmaf(wgt, ia, outr[o]);
                         if (hasB) ib = fmaf(wgt, ib, outr[o + p.obs]);

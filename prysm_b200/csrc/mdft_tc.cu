@@ -898,7 +898,7 @@ int pick_splits(int ny) {
     // stage 2 has only (Mx/128)*(2My/256) tiles; split its long contraction (2*Ny) to fill the GPU
     const long long kblocks = 2LL * ny / BK;
     int s = 8;
-    while (s > 1 && (kblocks % s != 0 || kblocks / s < 4)) s >>= 1;
+    while (s > 1 && (kblocks % s != 0 || kblocks / s < 4 * (32 / BK))) s >>= 1;   // at least 128 K elements per split
     return s;
 }
 
@@ -956,10 +956,13 @@ extern "C" int pb_mdft_tc_apply(pb_handle_t hh, const void* ExB_hi, const void* 
     float* ws = t1 + 2LL * ny * mx;
     {   // stage 1: T1^T(mx, ny) = (a @ Ex^T)^T : M = ny rows of a, N = 2*mx expanded basis rows, K = 2*nx
         GemmParams gp{(int)(2LL * nx / BK), chunk, 0, conv_b, t1, nullptr, (long long)ny, 0};
-        // stream-K when the tile grid does not fill the SMs evenly (C3: 128 tiles on 148 SMs); PB_MDFT_STREAMK=0 disables it
+        // stream-K when the tile grid leaves a good part of the SMs idle (1024^2 <-> 1024^2: 64 tiles on 148 SMs, 371 -> 346 us
+        // for the coronagraph round trip); at C3 (128 tiles) it is neutral -- 358.7 against 356.5 us -- and not used.
+        // PB_MDFT_STREAMK=0 disables it, =2 forces it wherever it is legal.
         static const int streamk = [] { const char* e = getenv("PB_MDFT_STREAMK"); return e ? atoi(e) : 1; }();
         const int tiles1 = (ny / BM) * (2 * mx / BN);
         const bool sk_ok = streamk && !pair && gp.kblocks % chunk == 0 && tiles1 % h->sm_count != 0 &&
+                           (streamk >= 2 || 5 * tiles1 < 4 * h->sm_count) &&
                            (long long)tiles1 * (gp.kblocks / chunk) >= 4LL * h->sm_count;
         if (sk_ok) {
             char* skw = reinterpret_cast<char*>(ws + (long long)splits * 2 * my * mx);
