@@ -131,6 +131,20 @@ int pb_czt_axis_intensity(pb_handle_t h, int dtype, const void* in, int ny, int 
                           int out_off, int n_out, double scale, int out_kind, double weight, void* out,
                           long long out_ld, void* stream);
 
+/* ---- the wavelength loop of an incoherent (polychromatic) PSF as one call -------------------------------------
+ * plane(m,m) += sum_i weight_i * | CZT_i( amp * exp(i * kscale_i * opd) ) |^2  over n_units wavelengths of a square n x n
+ * pupil on a common square m x m focal grid.  Replaces, per wavelength, Wavefront.from_amp_and_phase
+ * (prysm/propagation/wavefront.py:59-79) -> prepare_executor(kind='czt') (propagation/dft.py:69-117, fttools.py:257-291)
+ * -> focus_dft (fttools.py:296-325) -> .intensity (wavefront.py:147-151) and the running weighted sum of
+ * sum_of_2d_modes (polynomials/fitting.py:37) -- the loop of docs/source/how-tos/Polychromatic Propagation.ipynb:86-98.
+ * units: n_units records of 8 doubles on the HOST: kscale (phase per unit of opd), then the pb_czt_plan scalars shift,
+ * alpha, xc, f0, df of the (square, centred) geometry, the executor norm, the weight.  K: Bluestein length, a power of
+ * two >= n + m - 1.  The plan of unit i+1 is built on the handle's helper stream while unit i transforms.
+ * work: pb_polychromatic_czt_work_bytes(dtype, n, m, K) bytes, 256-byte aligned.  plane: real (float / double). */
+long long pb_polychromatic_czt_work_bytes(int dtype, int n, int m, int K);
+int pb_polychromatic_czt(pb_handle_t h, int dtype, const void* amp, int amp_kind, const void* opd, int n, int m, int K,
+                         int n_units, const double* units, void* work, void* plane, void* stream);
+
 /* The Bluestein pieces of one CZT axis built on the device from scalars (no host maths, no uploads):
  * b (N), post = a*phase (M), H = FFT_K(h) (K), Hadj (K) as consumed by pb_czt_axis.  alpha = dx*dfx,
  * shift = f[M/2]/df, xc = x[N/2], f0 = f[0], df the frequency step.  prysm/fttools.py:257-291, 372-389 */

@@ -35,6 +35,8 @@ SIGNATURES = {
     'pb_czt_plan': (_i, [_vp, _i, _i, _i, _i, _d, _d, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     'pb_czt_axis': (_i, [_vp, _i, _vp, _i, _i, _ll, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _vp, _ll, _vp]),
     'pb_czt_axis_intensity': (_i, [_vp, _i, _vp, _i, _i, _ll, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _i, _d, _vp, _ll, _vp]),
+    'pb_polychromatic_czt_work_bytes': (_ll, [_i, _i, _i, _i]),
+    'pb_polychromatic_czt': (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, C.POINTER(_d), _vp, _vp, _vp]),
     'pb_angular_spectrum': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     'pb_angular_spectrum_screen': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     'pb_angular_spectrum_vectors': (_i, [_vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp]),

@@ -222,6 +222,42 @@ def czt_plan(N, M, K, shift, alpha, sign, xc, f0, df, cdtype, dev):
     return b, post, H, Hadj
 
 
+def polychromatic_czt(amp, opd, m, K, units, plane):
+    """pb_polychromatic_czt: plane += sum_i weight_i |CZT_i(amp exp(i kscale_i opd))|^2 for the rows of `units`
+    (host float64 array (n_units, 8): kscale, shift, alpha, xc, f0, df, norm, weight) -- one library call for the loop."""
+    import numpy as np
+    opd = opd.contiguous()
+    n = opd.shape[0]
+    if opd.ndim != 2 or opd.shape[1] != n:
+        raise ValueError('a square OPD array is required')
+    rdt = opd.dtype
+    if rdt not in _CPLX_OF:
+        raise ValueError('opd must be float32 or float64')
+    if amp is None:
+        amp_kind, amp_t = capi.AMP_NONE, None
+    elif amp.dtype in (torch.bool, torch.uint8):
+        amp_kind, amp_t = capi.AMP_U8, amp.contiguous()
+    else:
+        amp_kind, amp_t = capi.AMP_REAL, amp.to(rdt).contiguous()
+    if amp_t is not None and tuple(amp_t.shape) != (n, n):
+        raise ValueError('amplitude and OPD shapes differ')
+    _check_out(plane, (m, m), rdt, opd.device, name='plane')
+    if not plane.is_contiguous():
+        raise ValueError('`plane` must be contiguous')
+    units = np.ascontiguousarray(units, dtype=np.float64)
+    if units.ndim != 2 or units.shape[1] != 8:
+        raise ValueError('units must have shape (n_units, 8)')
+    code = _CODE[_CPLX_OF[rdt]]
+    nbytes = int(lib.pb_polychromatic_czt_work_bytes(code, n, int(m), int(K)))
+    work = torch.empty(nbytes + 256, dtype=torch.uint8, device=opd.device)
+    off = (-work.data_ptr()) % 256
+    h, st = _ctx(opd)
+    import ctypes
+    h.check(lib.pb_polychromatic_czt(h.ptr, code, _p(amp_t), amp_kind, _p(opd), n, int(m), int(K), int(units.shape[0]),
+                                     units.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), work.data_ptr() + off, _p(plane), st))
+    return plane
+
+
 def czt_axis(a, K, axis, pre_e, H, post_e, out_off, n_out, scale=1.0, pre_conj=False, post_conj=False,
              out_kind=capi.OUT_COMPLEX, weight=1.0, out=None):
     """pb_czt_axis: (a*pre_e) -> FFT_K -> *H -> IFFT_K -> [out_off:out_off+n_out] -> *post_e*scale along `axis`.

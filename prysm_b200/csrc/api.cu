@@ -51,6 +51,8 @@ extern "C" int pb_destroy(pb_handle_t hh) {
     cudaDeviceSynchronize();
     for (auto& kv : h->tables) cudaFree(kv.second);
     for (int i = 0; i < 3; ++i) if (h->scratch[i]) cudaFree(h->scratch[i]);
+    for (auto& e : h->side_ev) if (e) cudaEventDestroy(e);
+    if (h->side) cudaStreamDestroy(h->side);
     delete h;
     return PB_OK;
 }

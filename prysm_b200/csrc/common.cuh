@@ -82,6 +82,10 @@ struct Handle {
     // (= per device and stream), never a process-wide static.
     std::set<const void*> attr_done;
     std::map<MapKey, CUtensorMap> maps;   // TMA descriptors by (base pointer, geometry)
+    // helper stream + events of the entry points that overlap small preparatory launches with the main sequence
+    // (pb_polychromatic_czt: the Bluestein plan of unit i+1 beside the transforms of unit i); created on first use
+    cudaStream_t side = nullptr;
+    cudaEvent_t side_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // Makes the handle's device current for the duration of an entry point and restores the caller's device on

@@ -2,6 +2,7 @@
 // phase-screen synthesis, |.|^2 (+ weighted accumulate), separable multiplies, weighted mode
 // sum, OTF normalisation, first moments, angular-spectrum factor vectors, MDFT bases.
 #include "common.cuh"
+#include "czt.cuh"
 
 namespace pb {
 
@@ -347,22 +348,31 @@ extern "C" int pb_encircled_energy(pb_handle_t hh, int dtype, const void* mtf, i
     return PB_OK;
 }
 
-extern "C" int pb_czt_plan(pb_handle_t hh, int dtype, int N, int M, int K, double shift, double alpha, int sign, double xc,
-                           double f0, double df, void* b, void* post, void* H, void* Hadj, void* stream) {
-    PB_HANDLE(hh);
-    if (N < 1 || M < 1 || K < N + M - 1 || (sign != 1 && sign != -1) || !b || !post || !H || !Hadj)
-        return fail(h, PB_ERR_INVALID, "bad czt plan arguments");
+int pb::czt_plan_impl(Handle* h, pb_handle_t hh, int dtype, int N, int M, int K, double shift, double alpha, int sign, double xc,
+                      double f0, double df, void* b, void* post, void* H, void* Hadj, void* hk, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int n = std::max(K, std::max(N, M));
-    void* hk = nullptr;
-    PB_TRY(ensure_scratch(h, 2, (size_t)K * csize(dtype), &hk));
     if (dtype == PB_C64) czt_plan_kernel<float><<<(n + 255) / 256, 256, 0, st>>>(N, M, K, shift, alpha, sign, xc, f0, df, (float2*)b, (float2*)post, (float2*)hk);
     else czt_plan_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(N, M, K, shift, alpha, sign, xc, f0, df, (double2*)b, (double2*)post, (double2*)hk);
     PB_LAUNCH_CHECK(h);
     PB_TRY(pb_fft1(hh, dtype, hk, 1, K, K, 1, K, -1, 1.0, H, K, stream));   // H = FFT_K(h)
-    if (dtype == PB_C64) czt_hadj_kernel<float><<<(K + 255) / 256, 256, 0, st>>>(N, K, (const float2*)H, (float2*)Hadj);
-    else czt_hadj_kernel<double><<<(K + 255) / 256, 256, 0, st>>>(N, K, (const double2*)H, (double2*)Hadj);
-    PB_LAUNCH_CHECK(h);
+    if (Hadj) {
+        if (dtype == PB_C64) czt_hadj_kernel<float><<<(K + 255) / 256, 256, 0, st>>>(N, K, (const float2*)H, (float2*)Hadj);
+        else czt_hadj_kernel<double><<<(K + 255) / 256, 256, 0, st>>>(N, K, (const double2*)H, (double2*)Hadj);
+        PB_LAUNCH_CHECK(h);
+    }
     return PB_OK;
+}
+
+extern "C" int pb_czt_plan(pb_handle_t hh, int dtype, int N, int M, int K, double shift, double alpha, int sign, double xc,
+                           double f0, double df, void* b, void* post, void* H, void* Hadj, void* stream) {
+    PB_HANDLE(hh);
+    (void)st;
+    if (N < 1 || M < 1 || K < N + M - 1 || (sign != 1 && sign != -1) || !b || !post || !H || !Hadj)
+        return fail(h, PB_ERR_INVALID, "bad czt plan arguments");
+    void* hk = nullptr;
+    PB_TRY(ensure_scratch(h, 2, (size_t)K * csize(dtype), &hk));
+    return czt_plan_impl(h, hh, dtype, N, M, K, shift, alpha, sign, xc, f0, df, b, post, H, Hadj, hk, stream);
 }
 
 extern "C" int pb_angular_spectrum_vectors(pb_handle_t hh, int dtype, int ky, int kx, double wvl_um, double dx_mm,

@@ -5,6 +5,7 @@
 
 #include "axis_pass.cuh"
 #include "fft_tuned.cuh"
+#include "czt.cuh"
 
 namespace pb {
 
@@ -285,7 +286,7 @@ extern "C" int pb_axis_dft(pb_handle_t hh, int dtype, const void* in, int ny, in
     return axis_dft(h, p, st);
 }
 
-static int czt_axis_impl(Handle* h, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int K,
+int pb::czt_axis_impl(Handle* h, int dtype, const void* in, int ny, int nx, long long in_ld, int axis, int K,
                          const void* pre_e, int pre_conj, const void* H, const void* post_e, int post_conj, int out_off,
                          int n_out, double scale, int out_kind, double weight, void* out, long long out_ld, void* stream) {
     if (dtype != PB_C64 && dtype != PB_C128) return fail(h, PB_ERR_INVALID, "dtype must be PB_C64 or PB_C128");

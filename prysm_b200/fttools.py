@@ -165,6 +165,24 @@ class _CztAxis:
         self.Hadj = np.conj(H) * _expi(-(N - 1) * k / K)
 
 
+def czt_axis_scalars(xv, fv, sign=-1):
+    """The plan of one chirp-z axis as scalars: [(input offset, (n, M, K, shift, alpha, sign, xc, f0, df)), ...] -- one
+    entry, or two half-length ones when N + M - 1 exceeds the register engine's longest transform (see CZT.__init__).
+    prysm/fttools.py:257-291 builds the same quantities as arrays on the host."""
+    N, M = len(xv), len(fv)
+    d, df = float(xv[1] - xv[0]), float(fv[1] - fv[0])
+    K = next_fast_len(N + M - 1)
+    if K > _ENGINE_MAX_K and N % 2 == 0 and next_fast_len(N // 2 + M - 1) <= _ENGINE_MAX_K:
+        parts = [(0, N // 2), (N // 2, N // 2)]
+    else:
+        parts = [(0, N)]
+    out = []
+    for start, n in parts:
+        sub = xv[start:start + n]
+        out.append((start, (n, M, next_fast_len(n + M - 1), float(fv[M // 2]) / df, d * df, sign, float(sub[n // 2]), float(fv[0]), df)))
+    return out
+
+
 class CZT:
     """Chirp-z transform with the MDFT interface (prysm/fttools.py:235-369).  Each axis is two
     fused passes: (chirp * data -> FFT_K -> * H) and (IFFT_K -> slice -> * chirp * phase)."""
@@ -185,19 +203,7 @@ class CZT:
         # both on the fast kernels (C5's final focus 4096 -> 512: 2 x K = 4096 instead of K = 8192 on the generic kernel).
         # The chirps, phase ramps and kernel spectra are built on the device from ten scalars per plan (fp64 phases):
         # constructing an executor per wavelength costs no host maths and no uploads.
-        def plans(xv, fv, N, M):
-            d, df = float(xv[1] - xv[0]), float(fv[1] - fv[0])
-            K = next_fast_len(N + M - 1)
-            if K > _ENGINE_MAX_K and N % 2 == 0 and next_fast_len(N // 2 + M - 1) <= _ENGINE_MAX_K:
-                parts = [(0, N // 2), (N // 2, N // 2)]
-            else:
-                parts = [(0, N)]
-            out = []
-            for start, n in parts:
-                sub = xv[start:start + n]
-                out.append((start, (n, M, next_fast_len(n + M - 1), float(fv[M // 2]) / df, d * df, sign, float(sub[n // 2]), float(fv[0]), df)))
-            return out
-        px, py = plans(x, fx, Nx, Mx), plans(y, fy, Ny, My)
+        px, py = czt_axis_scalars(x, fx, sign), czt_axis_scalars(y, fy, sign)
         built = {}
 
         def build(params):

@@ -71,6 +71,32 @@ def sharded_incoherent_sum(n_units, accumulate_unit, plane, group=None, dst=None
     return plane
 
 
+def _native_czt_units(kind, opd, mine, wavelengths, weights, dx, efl, focal_dx, focal_samples, shift):
+    """(K, units) for pb_polychromatic_czt -- units[i] = (kscale, shift, alpha, xc, f0, df, norm, weight) of this rank's i-th
+    wavelength -- or None when the configuration is not the one that entry point covers: CZT, square pupil and focal
+    grid, one Bluestein plan serving both axes, data in the configured precision."""
+    import os
+    from .fttools import czt_axis_scalars
+    if kind != 'czt' or os.environ.get('PB_POLY_NATIVE', '1') == '0':
+        return None
+    if opd.ndim != 2 or opd.shape[0] != opd.shape[1] or focal_samples[0] != focal_samples[1] or opd.dtype != config.real_dtype:
+        return None
+    rows, K = [], None
+    for i in mine:
+        w = float(wavelengths[i])
+        x, y, fx, fy = P.coordinates_for_focus(dx, tuple(opd.shape), focal_dx, focal_samples, w, efl, shift, dtype=np.float64)
+        sx, sy = czt_axis_scalars(x, fx), czt_axis_scalars(y, fy)
+        if len(sx) != 1 or sx != sy:
+            return None
+        _, (n, m, k, shf, alpha, _, xc, f0, df) = sx[0]
+        if K is None:
+            K = k
+        if k != K:
+            return None
+        rows.append((P.phase_prefix(w).imag, shf, alpha, xc, f0, df, (dx * focal_dx) / (w * efl), float(weights[i])))
+    return (K if K is not None else 0), np.asarray(rows, dtype=np.float64).reshape(-1, 8)
+
+
 def polychromatic_psf(amplitude, phase, wavelengths, weights, dx, efl, focal_dx, focal_samples, kind='czt',
                       shift=(0, 0), group=None, dst=None, shard=True):
     """Weighted incoherent PSF over `wavelengths` on a common focal grid.
@@ -95,11 +121,22 @@ def polychromatic_psf(amplitude, phase, wavelengths, weights, dx, efl, focal_dx,
     plane = torch.zeros(tuple(focal_samples), dtype=config.real_dtype, device=opd.device)
     cplx_of_plane = torch.complex64 if plane.dtype == torch.float32 else torch.complex128
 
+    rank, world = _world(group) if shard else (0, 1)
+    mine = shard_units(len(wavelengths), rank, world)
+
+    # CZT on a square, centred geometry (every BASELINE configuration): the whole loop of this rank is ONE native call
+    # (pb_polychromatic_czt) -- per wavelength six scalars instead of ~7 library calls, two temporaries and an event, so the
+    # loop is bound by its ~220 us of kernels per wavelength and not by the host's launch rate (203 ... 328 us per wavelength
+    # were measured through the Python loop below on two boxes).  PB_POLY_NATIVE=0 selects the Python loop.
+    units = _native_czt_units(kind, opd, mine, wavelengths, weights, dx, efl, focal_dx, focal_samples, shift)
+    if units is not None:
+        if mine:
+            _ops.polychromatic_czt(amp, opd, focal_samples[0], units[0], units[1], plane)
+        return sharded_incoherent_sum(0, None, plane, group=group, dst=dst, shard=shard)
+
     # Each wavelength has its own executor (the chirp rate dx*dfx/(wvl*efl) changes), built on the device from scalars in
     # three small, latency-bound launches (~20 us).  They are issued on a SIDE stream one unit ahead, so the next
     # wavelength's plan is ready when the current wavelength's transforms finish instead of sitting between them.
-    rank, world = _world(group) if shard else (0, 1)
-    mine = shard_units(len(wavelengths), rank, world)
     main = torch.cuda.current_stream(opd.device)
     side = _side_stream(opd.device)
     shape = tuple(opd.shape)

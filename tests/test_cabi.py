@@ -108,7 +108,7 @@ def test_every_entry_point_rejects_a_null_handle():
     boundary as a crash).  Needs no GPU -- the check is the first thing every call does."""
     from prysm_b200 import _capi
     no_handle = {'pb_create', 'pb_destroy', 'pb_last_error', 'pb_version', 'pb_launch_count', 'pb_mdft_work_elems',
-                 'pb_mdft_tc_supported', 'pb_mdft_tc_work_bytes'}
+                 'pb_mdft_tc_supported', 'pb_mdft_tc_work_bytes', 'pb_polychromatic_czt_work_bytes'}
     checked = 0
     for name, (_, args) in _capi.SIGNATURES.items():
         if name in no_handle:

@@ -102,3 +102,42 @@ def test_polychromatic_two_nccl_ranks(pb):
     wvls = np.linspace(0.5, 0.7, 5)
     ref = reference_sum(amp, opd, wvls, np.full(5, 0.2), dx, 100.0, 2.5, 128, 'czt')
     assert rel_linf(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize('precision,N,M', [(32, 512, 256), (32, 1024, 1024), (64, 256, 128)])
+def test_native_wavelength_loop_matches_the_python_loop(pb, precision, N, M):
+    """pb_polychromatic_czt (the whole loop in one library call, plans one unit ahead on the handle's helper stream) runs
+    the same kernels with the same scalars as the per-wavelength Python loop: identical planes.  Called twice to cover the
+    reuse of the plan buffers and events across calls."""
+    from prysm_b200.polychromatic import polychromatic_psf
+    pb.config.precision = precision
+    rdt = np.float32 if precision == 32 else np.float64
+    amp, opd, dx = O.synthetic_pupil(N, rdt)
+    wvls = np.linspace(0.5, 0.7, 5)
+    wts = np.array([0.1, 0.3, 0.2, 0.25, 0.15])
+    try:
+        os.environ['PB_POLY_NATIVE'] = '0'
+        loop = polychromatic_psf(amp, opd, wvls, wts, dx, 100.0, 2.5, M, kind='czt')
+        os.environ['PB_POLY_NATIVE'] = '1'
+        native = polychromatic_psf(amp, opd, wvls, wts, dx, 100.0, 2.5, M, kind='czt')
+        again = polychromatic_psf(amp, opd, wvls, wts, dx, 100.0, 2.5, M, kind='czt')
+    finally:
+        os.environ.pop('PB_POLY_NATIVE', None)
+        pb.config.precision = 64
+    assert native.dtype == loop.dtype and tuple(native.shape) == (M, M)
+    assert torch.equal(native, again)
+    assert torch.equal(native, loop)
+
+
+def test_native_loop_argument_checks(pb):
+    from prysm_b200 import _ops
+    pb.config.precision = 32
+    opd = torch.zeros((64, 64), dtype=torch.float32, device='cuda')
+    units = np.zeros((1, 8))
+    with pytest.raises(ValueError):
+        _ops.polychromatic_czt(None, opd, 32, 128, units, torch.zeros((32, 32), dtype=torch.float64, device='cuda'))   # plane dtype
+    with pytest.raises(ValueError):
+        _ops.polychromatic_czt(None, opd, 32, 128, np.zeros((1, 7)), torch.zeros((32, 32), dtype=torch.float32, device='cuda'))
+    with pytest.raises(ValueError):   # K < n + m - 1: rejected by the library (PB_ERR_INVALID)
+        _ops.polychromatic_czt(None, opd, 32, 64, units, torch.zeros((32, 32), dtype=torch.float32, device='cuda'))
+    pb.config.precision = 64

@@ -17,7 +17,7 @@ import pytest
 import torch
 
 import prysm_oracle as O
-from conftest import load_golden
+from conftest import load_golden, within
 
 pytestmark = pytest.mark.gpu
 HeNe = 0.6328
@@ -49,15 +49,15 @@ def test_c4_czt_fields_and_incoherent_sum_vs_reference(pb):
         f = host(wf.focus_dft(wf.prepare_executor(100.0, 2.5, M, kind='czt')).data)
         den = float(g[tag + 'absmax'])
         assert f.shape == (M, M)
-        assert np.abs(f[::64, ::64] - g[tag + 'field_stride']).max() / den < 5.5e-7
-        assert np.abs(f[cy - 32:cy + 32, cy - 32:cy + 32] - g[tag + 'field_win']).max() / den < 5.5e-7
+        within(f'c4.{tag}field_stride', np.abs(f[::64, ::64] - g[tag + 'field_stride']).max() / den, 5.5e-7)
+        within(f'c4.{tag}field_window', np.abs(f[cy - 32:cy + 32, cy - 32:cy + 32] - g[tag + 'field_win']).max() / den, 5.5e-7)
         I = (f.real.astype(np.float64) ** 2 + f.imag.astype(np.float64) ** 2).sum()
         assert I == pytest.approx(float(g[tag + 'I_sum']), rel=1e-6)
     from prysm_b200.polychromatic import polychromatic_psf
     tot = host(polychromatic_psf(amp, opd, [0.5, 0.7], [0.25, 0.75], dx, 100.0, 2.5, M, kind='czt')).astype(np.float64)
     smax = float(g['sum_max'])
-    assert np.abs(tot[::64, ::64] - g['sum_stride']).max() / smax < 1e-6
-    assert np.abs(tot[cy - 32:cy + 32, cy - 32:cy + 32] - g['sum_win']).max() / smax < 1e-6
+    within('c4.sum_stride', np.abs(tot[::64, ::64] - g['sum_stride']).max() / smax, 1e-6)
+    within('c4.sum_window', np.abs(tot[cy - 32:cy + 32, cy - 32:cy + 32] - g['sum_win']).max() / smax, 1e-6)
     assert tot.sum() == pytest.approx(float(g['sum_total']), rel=1e-6)
 
 
@@ -75,15 +75,15 @@ def test_c5_screen_and_free_space_plane_vs_reference(pb):
     den = float(g['absmax'])
     c = N // 2
     assert out.shape == (N, N)
-    assert np.abs(out[::128, ::128] - g['field_stride']).max() / den < 1e-6
-    assert np.abs(out[c - 32:c + 32, c - 32:c + 32] - g['field_win']).max() / den < 1e-6
-    assert np.abs(out[c, 1000:1100] - g['edge']).max() / den < 1e-6
+    within('c5.plane_stride', np.abs(out[::128, ::128] - g['field_stride']).max() / den, 1e-6)
+    within('c5.plane_window', np.abs(out[c - 32:c + 32, c - 32:c + 32] - g['field_win']).max() / den, 1e-6)
+    within('c5.plane_edge', np.abs(out[c, 1000:1100] - g['edge']).max() / den, 1e-6)
     E = (out.real.astype(np.float64) ** 2 + out.imag.astype(np.float64) ** 2).sum()
     assert E == pytest.approx(float(g['E_out']), rel=1e-6)
     # the chain's final focus: CZT 4096^2 -> 512^2
     foc = host(plane.focus_dft(plane.prepare_executor(100.0, float(g['focal_dx']), 512, kind='czt')).data)
     fden = float(g['focus_absmax'])
-    assert np.abs(foc[256 - 32:256 + 32, 256 - 32:256 + 32] - g['focus_win']).max() / fden < 6.5e-7
-    assert np.abs(foc[::16, ::16] - g['focus_stride']).max() / fden < 6.5e-7
+    within('c5.focus_window', np.abs(foc[256 - 32:256 + 32, 256 - 32:256 + 32] - g['focus_win']).max() / fden, 6.5e-7)
+    within('c5.focus_stride', np.abs(foc[::16, ::16] - g['focus_stride']).max() / fden, 6.5e-7)
     If = (foc.real.astype(np.float64) ** 2 + foc.imag.astype(np.float64) ** 2).sum()
     assert If == pytest.approx(float(g['focus_I_sum']), rel=2e-6)
