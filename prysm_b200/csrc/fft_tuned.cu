@@ -691,6 +691,32 @@ __global__ void __launch_bounds__((COLS ? TP : 1) * L / 16, (RT && (!COLS || TP 
     // stall).  vin / vout: unit line stride, even pitch, 16-byte aligned base, both lines present (host: dispatch_axis_reg).
     const bool vin = COLS && (DENSE || ((p.batch_contiguous & 2) && hasB));
     const bool vout = COLS && (DENSE || ((p.batch_contiguous & 4) && hasB));
+    if (DENSE) {
+        // L2 prefetch of the lines of the CTA that will run `pf` CTAs later (= the number of resident CTAs): its input loads
+        // then hit L2 instead of paying the DRAM latency at the head of a CTA that cannot overlap loading with computing
+        const int pf = p.batch_contiguous >> 8;
+        if (pf) {
+            const int nb0 = ((int)blockIdx.x + pf) * (COLS ? TP : 1) * 2;
+            if (nb0 < p.nb) {
+                if (!COLS) {
+                    if (threadIdx.x < 2) {      // one bulk prefetch per line (contiguous: ies == 1), and of its screen row
+                        const float2* src = reinterpret_cast<const float2*>(p.in) + (long long)(nb0 + threadIdx.x) * p.ibs;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(L * sizeof(float2))) : "memory");
+                        if (PM) {
+                            const float2* sm = reinterpret_cast<const float2*>(p.pre_mat) + (long long)(nb0 + threadIdx.x) * p.pmi_bs;
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sm), "r"((uint32_t)(L * sizeof(float2))) : "memory");
+                        }
+                    }
+                } else if (c == 0) {            // the 32-byte segments (TP = 2: four columns) of the next tile, one thread per segment
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) {
+                        const float2* src = reinterpret_cast<const float2*>(p.in) + (long long)nb0 * p.ibs + (long long)(n * NT + t) * p.ies;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(src) : "memory");
+                    }
+                }
+            }
+        }
+    }
     const float2* __restrict__ in = reinterpret_cast<const float2*>(p.in);
     const float2* __restrict__ pre_e = reinterpret_cast<const float2*>(p.pre_e);
     const float2* __restrict__ pre_b = reinterpret_cast<const float2*>(p.pre_b);
@@ -943,6 +969,20 @@ int launch_axis_reg(Handle* h, const AxisPass& p, cudaStream_t st) {
     PB_TRY(get_plain_plan<L>(h, &tw1, &tw2));
     const int lines_per_cta = 2 * TP;
     const int grid = (p.nb + lines_per_cta - 1) / lines_per_cta;
+    if (DENSE) {   // L2 prefetch distance = resident CTAs (PB_AXIS_PREFETCH: bit 0 row passes, bit 1 column passes)
+        static const int pf_mode = env_int("PB_AXIS_PREFETCH", 0);
+        const size_t unified = 256 * 1024, l1_keep = 64 * 1024;
+        const int regs_ctas = COLS ? 1 : 2;
+        const int ctas = std::min<int>(regs_ctas, std::max<int>(1, (int)((unified - l1_keep) / (smem + 1024))));
+        const bool on = COLS ? (pf_mode & 2) != 0 : ((pf_mode & 1) != 0 && p.ies == 1 && (!PM || p.pmi_es == 1));
+        if (on) {
+            AxisPass q = p;
+            q.batch_contiguous = (p.batch_contiguous & 255) | ((ctas * h->sm_count) << 8);
+            axis_reg_kernel<L, INV, COLS, TP, RT, PM, DENSE><<<grid, TP * G::NT, smem, st>>>(q, tw1, tw2);
+            PB_LAUNCH_CHECK(h);
+            return PB_OK;
+        }
+    }
     axis_reg_kernel<L, INV, COLS, TP, RT, PM, DENSE><<<grid, TP * G::NT, smem, st>>>(p, tw1, tw2);
     PB_LAUNCH_CHECK(h);
     return PB_OK;
