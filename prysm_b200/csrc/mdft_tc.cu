@@ -340,6 +340,7 @@ struct SkParams {
     GemmParams g;        // g.kblocks = K-blocks per TILE; g.chunk divides it; g.mode = 0
     int ntn;             // tiles along N
     int ntiles;          // tiles of the launch
+    float scale;         // applied in the owner's store (1 for stage 1, the executor norm for stage 2)
     float* part;         // [gridDim.x][256][128] partial tiles, column-major inside the tile
     int* flags;          // [gridDim.x] epilogue warps of CTA g that have published its partial (zeroed before the launch)
 };
@@ -542,7 +543,7 @@ tc_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
 #pragma unroll
                 for (int cc = 0; cc < 128; cc += 2) {
                     const long long o = (long long)((nb + cc) >> 1) * p.ldo + m;
-                    hi[o] = make_float2(tot[cc], tot[cc + 1]);
+                    hi[o] = make_float2(sp.scale * tot[cc], sp.scale * tot[cc + 1]);
                 }
             }
             u += nseg;
@@ -853,7 +854,7 @@ constexpr long long SK_WORK_BYTES = (long long)SK_MAX_CTAS * BM * BN * 4 + 4096;
 
 // stream-K form (mode 0 only): `work` = SK_WORK_BYTES of scratch
 int launch_gemm_sk(Handle* h, const float* A, const float* Bhi, const float* Blo, int M, int N, long long K,
-                   const GemmParams& gp, void* work, cudaStream_t st) {
+                   const GemmParams& gp, float scale, void* work, cudaStream_t st) {
     CUtensorMap mAhi, mBhi, mBlo;
     PB_TRY(make_map(h, &mAhi, A, M, K, BM));
     PB_TRY(make_map(h, &mBhi, Bhi, N, K, BN));
@@ -862,6 +863,7 @@ int launch_gemm_sk(Handle* h, const float* A, const float* Bhi, const float* Blo
         PB_CUDA(h, cudaFuncSetAttribute(tc_gemm_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     SkParams sp;
     sp.g = gp;
+    sp.scale = scale;
     sp.ntn = N / BN;
     sp.ntiles = (M / BM) * (N / BN);
     sp.part = reinterpret_cast<float*>(work);
@@ -962,16 +964,36 @@ extern "C" int pb_mdft_tc_apply(pb_handle_t hh, const void* ExB_hi, const void* 
         static const int streamk = [] { const char* e = getenv("PB_MDFT_STREAMK"); return e ? atoi(e) : 1; }();
         const int tiles1 = (ny / BM) * (2 * mx / BN);
         const bool sk_ok = streamk && !pair && gp.kblocks % chunk == 0 && tiles1 % h->sm_count != 0 &&
-                           (streamk >= 2 || 5 * tiles1 < 4 * h->sm_count) &&
+                           (streamk >= 2 || (5 * tiles1 < 4 * h->sm_count && 4 * tiles1 >= h->sm_count)) &&
                            (long long)tiles1 * (gp.kblocks / chunk) >= 4LL * h->sm_count;
         if (sk_ok) {
             char* skw = reinterpret_cast<char*>(ws + (long long)splits * 2 * my * mx);
             skw += (16 - ((uintptr_t)skw & 15)) & 15;
-            PB_TRY(launch_gemm_sk(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, gp, skw, st));
+            PB_TRY(launch_gemm_sk(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, gp, 1.0f, skw, st));
         } else if (pair && ny % (2 * BM) == 0) PB_TRY(launch_gemm_pair(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
         else PB_TRY(launch_gemm(h, (const float*)a, (const float*)ExB_hi, (const float*)ExB_lo, ny, 2 * mx, 2LL * nx, 1, gp, st));
     }
-    {   // stage 2: out^T' = T1^T' @ Ey'^T : M = mx, N = 2*my, K = 2*ny, split-K partials transposed into ws[s][2my][mx]
+    // stage 2: out^T' = T1^T' @ Ey'^T : M = mx, N = 2*my, K = 2*ny.  Few tiles and a long contraction: stream-K over all SMs
+    // with the owner's store landing the result, scaled by `norm`, directly in (My, Mx) complex orientation (same index
+    // arithmetic as stage 1's transposed complex store with ldo = mx) -- no partial planes, no reduce kernel: the 1024^2 <->
+    // 1024^2 coronagraph round trip went from 340 to 249 us.  With very few tiles (C3: 16, i.e. 9 pieces per tile) the owner's
+    // serial gather costs more than it saves (373.6 against 357.6 us): those, shapes too small for it, and PB_MDFT_STREAMK=0
+    // take split-K + reduce.
+    {
+        static const int streamk2 = [] { const char* e = getenv("PB_MDFT_STREAMK"); return e ? atoi(e) : 1; }();
+        static const int pair2 = [] { const char* e = getenv("PB_MDFT_PAIR"); return e ? atoi(e) : 0; }();
+        const int kb2 = (int)(2LL * ny / BK);
+        const int tiles2 = (mx / BM) * (2 * my / BN);
+        if (streamk2 && !pair2 && kb2 % chunk == 0 && tiles2 % h->sm_count != 0 &&
+            (streamk2 >= 2 || (5 * tiles2 < 4 * h->sm_count && 4 * tiles2 >= h->sm_count)) &&   // 2-4 pieces per tile: the owner's gather stays short
+            (long long)tiles2 * (kb2 / chunk) >= 4LL * h->sm_count) {
+            GemmParams gp{kb2, chunk, 0, 0, reinterpret_cast<float*>(out), nullptr, (long long)mx, 0};
+            char* skw = reinterpret_cast<char*>(ws + (long long)splits * 2 * my * mx);
+            skw += (16 - ((uintptr_t)skw & 15)) & 15;
+            return launch_gemm_sk(h, t1, (const float*)EyB_hi, (const float*)EyB_lo, mx, 2 * my, 2LL * ny, gp, (float)norm, skw, st);
+        }
+    }
+    {   // split-K partials transposed into ws[s][2my][mx]
         GemmParams gp{(int)(2LL * ny / BK / splits), chunk, 1, conv_b, ws, nullptr, (long long)mx, 2LL * my * mx};
         if (pair && mx % (2 * BM) == 0) PB_TRY(launch_gemm_pair(h, t1, (const float*)EyB_hi, (const float*)EyB_lo, mx, 2 * my, 2LL * ny, splits, gp, st));
         else PB_TRY(launch_gemm(h, t1, (const float*)EyB_hi, (const float*)EyB_lo, mx, 2 * my, 2LL * ny, splits, gp, st));
