@@ -1,6 +1,6 @@
 """Build libprysm_b200.so in-tree with nvcc for sm_100a.
 
-    python -m prysm_b200.build [--force] [--verbose]
+    python prysm_b200/build.py [--force] [--verbose]      (by path: importing the package needs the library this builds)
 
 The shared library lands in prysm_b200/_lib/ (git-ignored, but it travels to the GPU box
 with the gpurun snapshot).  No torch extension machinery: the boundary is a plain C ABI.

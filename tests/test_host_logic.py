@@ -1,6 +1,7 @@
 """CPU: host-side logic of the mirror API that needs no kernel launch -- argument checks,
 error types / messages, shape and sample-spacing bookkeeping, executor planning."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -154,3 +155,40 @@ def test_handle_cache_is_bounded_and_pins_graph_streams(monkeypatch):
     assert len(closed) == 1
     _capi.release_handle(0, 100)
     assert first in closed and (0, 100) not in _capi._handles and (0, 100) not in _capi._pinned
+
+
+def test_native_polychromatic_units_host_logic():
+    """polychromatic._native_czt_units: the records handed to pb_polychromatic_czt are the scalars the CZT executor itself
+    would use (same helper), and every configuration the native loop does not cover falls back (None)."""
+    import torch
+    import prysm_b200 as pb
+    from prysm_b200 import polychromatic as poly, propagation as P
+    from prysm_b200.fttools import czt_axis_scalars
+    pb.config.precision = 32
+    try:
+        N, M = 256, 128
+        opd = torch.zeros((N, N), dtype=torch.float32)
+        wv = np.array([0.5, 0.6, 0.7]); wt = np.array([0.2, 0.3, 0.5])
+        K, units = poly._native_czt_units('czt', opd, [0, 2], wv, wt, 0.04, 100.0, 2.5, (M, M), (0, 0))
+        assert K == 512 and units.shape == (2, 8) and units.dtype == np.float64
+        for row, i in zip(units, (0, 2)):
+            x, y, fx, fy = P.coordinates_for_focus(0.04, (N, N), 2.5, (M, M), float(wv[i]), 100.0, (0, 0), dtype=np.float64)
+            (_, (n, m, k, shift, alpha, sign, xc, f0, df)), = czt_axis_scalars(x, fx)
+            assert (n, m, k, sign) == (N, M, 512, -1)
+            assert row[0] == pytest.approx(2 * np.pi / (wv[i] * 1e3))                 # OPD [nm] -> radians
+            assert tuple(row[1:6]) == (shift, alpha, xc, f0, df)
+            assert row[6] == pytest.approx(0.04 * 2.5 / (wv[i] * 100.0)) and row[7] == wt[i]
+        assert poly._native_czt_units('czt', opd, [], wv, wt, 0.04, 100.0, 2.5, (M, M), (0, 0))[1].shape == (0, 8)
+        # not covered: other executors, rectangular grids, an off-axis window (x and y plans differ), mixed precision,
+        # a Bluestein length beyond the register engine (two half-length plans per axis), the opt-out switch
+        assert poly._native_czt_units('mdft', opd, [0], wv, wt, 0.04, 100.0, 2.5, (M, M), (0, 0)) is None
+        assert poly._native_czt_units('czt', opd, [0], wv, wt, 0.04, 100.0, 2.5, (M, M // 2), (0, 0)) is None
+        assert poly._native_czt_units('czt', opd, [0], wv, wt, 0.04, 100.0, 2.5, (M, M), (10.0, 0.0)) is None
+        assert poly._native_czt_units('czt', opd.double(), [0], wv, wt, 0.04, 100.0, 2.5, (M, M), (0, 0)) is None
+        big = torch.zeros((4096, 4096), dtype=torch.float32)
+        assert poly._native_czt_units('czt', big, [0], wv, wt, 0.0025, 100.0, 2.5, (512, 512), (0, 0)) is None
+        os.environ['PB_POLY_NATIVE'] = '0'
+        assert poly._native_czt_units('czt', opd, [0], wv, wt, 0.04, 100.0, 2.5, (M, M), (0, 0)) is None
+    finally:
+        os.environ.pop('PB_POLY_NATIVE', None)
+        pb.config.precision = 64
