@@ -310,13 +310,34 @@ def angular_spectrum(field, k, ty=None, tx=None, tf=None, conj_tf=False, crop=No
     return out
 
 
+_AS_VECTORS = {}     # (shape, wvl, dx, z, dtype, device, stream) -> (ty, tx); most recently used last
+
+
 def angular_spectrum_vectors(shape, wvl, dx, z, cdtype, dev):
+    """The two separable factors of the free-space transfer function (pb_angular_spectrum_vectors).  A plane-to-plane chain
+    asks for the same pair at every step (same grid, wavelength and dz): the last few pairs are kept per stream (they are
+    read-only, 8 or 16 bytes per sample of one axis), which takes two small launches out of every step of the chain.
+    Skipped while a CUDA graph is being captured (a captured graph must own the launches that fill what it reads)."""
     ky, kx = shape
+    dev = torch.device(dev)
+    capturing = torch.cuda.is_current_stream_capturing() if dev.type == 'cuda' else False
+    key = None
+    if not capturing and dev.type == 'cuda':
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        key = (int(ky), int(kx), float(wvl), float(dx), float(z), cdtype, idx, torch.cuda.current_stream(dev).cuda_stream)
+        hit = _AS_VECTORS.pop(key, None)
+        if hit is not None:
+            _AS_VECTORS[key] = hit
+            return hit
     ty = torch.empty(ky, dtype=cdtype, device=dev)
     tx = torch.empty(kx, dtype=cdtype, device=dev)
     h, st = _ctx(ty)
     h.check(lib.pb_angular_spectrum_vectors(h.ptr, _CODE[cdtype], ky, kx, float(wvl), float(dx), float(z),
                                             _p(ty), _p(tx), st))
+    if key is not None:
+        _AS_VECTORS[key] = (ty, tx)
+        while len(_AS_VECTORS) > 8:
+            _AS_VECTORS.pop(next(iter(_AS_VECTORS)))
     return ty, tx
 
 

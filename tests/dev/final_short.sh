@@ -13,3 +13,4 @@ d=json.loads(open('gpurun_out/final2_bench_1gpu.json').read().strip().splitlines
 print('value',round(d['value']),'frac',round(d['roofline']['frac'],3),'clocks',d['clocks']['sm_mhz'],'e2e',round(d['e2e']['value']))
 print('mdft',round(d['mdft_c3']['us_per_apply'],1),round(d['mdft_c3']['roofline']['frac'],3),'c4 us/wvl',round(d['c4_polychromatic']['us_per_wavelength_per_gpu'],1),'c5 us/plane',round(d['c5_free_space']['us_per_plane'],1),'fused_psf',round(d['fused_psf']['us_per_psf'],1))
 PY
+( timeout 200 python tools/bench_paths.py > gpurun_out/final2_paths.log 2>&1 ); cat gpurun_out/final2_paths.log
