@@ -201,7 +201,9 @@ long long pb_mdft_work_elems(int my, int ny, int mx, int nx, int adjoint, int le
  *   pb_mdft_tc_expand    : complex basis E (m,n) -> real expansions hi, lo, each (2m, 2n) fp32;
  *                          done once per executor for Ex and for Ey (prysm/fttools.py:187-191)
  *   pb_mdft_tc_apply     : out(my,mx) = norm * Ey @ a @ Ex^T   (prysm/fttools.py:201-207);
- *                          work: pb_mdft_tc_work_bytes() bytes of 1 KB-aligned device scratch */
+ *                          work: pb_mdft_tc_work_bytes() bytes of 16-byte aligned device scratch (the transposed
+ *                          intermediate, split-K partial planes, and the partial tiles + flags of the stream-K form
+ *                          that under-filled tile grids take) */
 int pb_mdft_tc_supported(int my, int ny, int mx, int nx);
 int pb_mdft_tc_expand(pb_handle_t h, const void* E, int m, int n, void* hi, void* lo, void* stream);
 long long pb_mdft_tc_work_bytes(int my, int ny, int mx, int nx);
