@@ -84,7 +84,7 @@ SIGNATURES = {
 def load_library(path=LIB_PATH):
     if not os.path.exists(path):
         raise ImportError(
-            f'{path} is missing: build it with `python -m prysm_b200.build` '
+            f'{path} is missing: build it with `python prysm_b200/build.py` '
             '(prysm_b200 has no CPU fallback)')
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
