@@ -290,7 +290,9 @@ def measure_mdft_c3(peaks):
             'us_per_apply': sec * 1e6, 'applies_per_s': 1.0 / sec, 'tensor_core_path': ex._tc is not None,
             'executor_build_plus_first_apply_ms': build_ms,
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                         'traffic': None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (measured, burst)',
+                         'traffic': None,
+                         'peak_source': ('MEASURED_PEAKS.json bf16_tflops (measured, burst)' if 'bf16_tflops' in peaks
+                                         else 'fallback 1590 TFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)'),
                          'algorithmic_flops_per_apply': flops, 'issued_tf32_tflops': 3 * ach,
                          'note': 'algorithmic flops vs the bf16 peak; the path issues 3 TF32 MMAs per product (TF32 runs at half the bf16 rate)'}}
 
